@@ -1,0 +1,42 @@
+"""Front-end driver: .kex source -> pipeline of SSTs.
+
+Mirrors `createProgram` / `buildTransducers` / `generateDirectSSTs`
+(src/KMC/Frontend/Commands.hs:50-115,159-180) for the `--act=false --la=false`
+configuration: parse, desugar, one transducer per pipeline stage, path-tree
+determinization, optional constant-propagation optimisation.
+"""
+from .kleenex import parse_kleenex, desugar
+from .fst import construct_transducer, run_lockstep, run_actions
+from .sst import sst_from_fst, optimize, run_sst
+
+
+def build_transducers(src: str):
+    pipeline, decls = parse_kleenex(src)
+    pl, rdecls = desugar(pipeline, decls)
+    return [construct_transducer(rdecls, ident) for ident in pl]
+
+
+def build_ssts(src: str, opt: int = 3):
+    """-> [SST] (one per pipeline stage), as `kexc compile --act=false
+    --la=false --opt <opt>` would determinize them."""
+    return [optimize(sst_from_fst(t), opt) for t in build_transducers(src)]
+
+
+def simulate_lockstep(src: str, data: bytes):
+    """`kexc simulate --sim=lockstep` (Commands.hs:277-289): returns output
+    bytes or None on reject."""
+    for t in build_transducers(src):
+        syms = run_lockstep(t, data)
+        if syms is None:
+            return None
+        data = run_actions(syms)
+    return data
+
+
+def simulate_sst(ssts, data: bytes):
+    """`kexc simulate --sim=sst` over a pipeline; None on reject."""
+    for s in ssts:
+        ok, data, _ = run_sst(s, data)
+        if not ok:
+            return None
+    return data

@@ -1,0 +1,380 @@
+"""FST -> streaming string transducer (path-tree determinization), SST
+optimisation and the reference SST interpreter.
+
+Restates src/KMC/Determinization.hs (all), src/KMC/TreeWriter.hs (the closure
+monad, as explicit tree rebuilding with a shared visited set),
+src/KMC/SymbolicSST.hs:72-136 (SST type, update normalisation),
+:182-331 (constant propagation `optimize`), :333-367 (enumeration) and
+:406-446 (`run`).  Single-symbol mode only (`--la=false`,
+Commands.hs:126,171): every transition consumes exactly one byte.
+
+Trees:   ("tip", w, state) | ("fork", w, (children...))
+Atoms:   ("v", var) | ("c", (bytes...)) | ("f",)      ("f",) = append input byte
+Vars:    tuples giving the root->leaf path of the tree node that owns the
+         register; () is the designated output register.  Tuple order is tree
+         pre-order, so an ancestor always sorts before its descendants.
+"""
+from . import byteset as BS
+from .fst import coarsest_predicate_set
+
+
+# ------------------------------------------------------------ tree plumbing
+def _tprepend(w, t):
+    if not w:
+        return t
+    if t[0] == "tip":
+        return ("tip", w + t[1], t[2])
+    return ("fork", w + t[1], t[2])
+
+
+def _bind(tree, k):
+    """joinTreeWriterT . fmap k (TreeWriter.hs:71-90): run continuation k on
+    every tip left to right, pruning failed branches and collapsing forks
+    with a single survivor."""
+    if tree is None:
+        return None
+    if tree[0] == "tip":
+        r = k(tree[2])
+        if r is None:
+            return None
+        return _tprepend(tree[1], r)
+    ts = []
+    for c in tree[2]:
+        r = _bind(c, k)
+        if r is not None:
+            ts.append(r)
+    if not ts:
+        return None
+    if len(ts) == 1:
+        return _tprepend(tree[1], ts[0])
+    return ("fork", tree[1], tuple(ts))
+
+
+def _reduce(tree):
+    """Hoist the longest common atom prefix of a fork's children into the
+    fork (Determinization.hs:63-71)."""
+    if tree is None or tree[0] == "tip":
+        return tree
+    ts = [_reduce(c) for c in tree[2]]
+    outs = [c[1] for c in ts]
+    n = min(len(o) for o in outs)
+    k = 0
+    while k < n and all(o[k] == outs[0][k] for o in outs):
+        k += 1
+    if k:
+        p = outs[0][:k]
+        ts = [(c[0], c[1][k:], c[2]) for c in ts]
+        return ("fork", tree[1] + p, tuple(ts))
+    return ("fork", tree[1], tuple(ts))
+
+
+def _tflat(tree):
+    if tree is None:
+        return []
+    if tree[0] == "tip":
+        return [tree[2]]
+    out = []
+    for c in tree[2]:
+        out.extend(_tflat(c))
+    return out
+
+
+def _closure(fst, tree):
+    """closureTree / closureTreeFunc (Determinization.hs:127-139): follow all
+    non-input transitions from every tip, sharing one visited set."""
+    vis = set()
+
+    def gen(q):
+        es = fst.eps.get(q)
+        if not es:
+            return ("tip", (), q)
+        ts = []
+        for out, q2 in es:
+            if q2 in vis:
+                continue
+            vis.add(q2)
+            sub = gen(q2)
+            if sub is not None:
+                ts.append(_tprepend((("c", tuple(out)),), sub))
+        if not ts:
+            return None
+        if len(ts) == 1:
+            return ts[0]
+        return ("fork", (), tuple(ts))
+
+    return _reduce(_bind(tree, gen))
+
+
+def _eof(fst, tree):
+    vis = set()
+
+    def k(q):
+        if fst.is_final(q) and q not in vis:
+            vis.add(q)
+            return ("tip", (), q)
+        return None
+
+    return _reduce(_bind(tree, k))
+
+
+def _consume(fst, p, tree):
+    vis = set()
+
+    def k(q):
+        hits = [(f, q2) for (p2, f, q2) in fst.sym.get(q, ()) if BS.is_subset(p, p2)]
+        if not hits:
+            return None
+        if len(hits) > 1:
+            raise NotImplementedError(
+                "Stepping for FSTs with read-fanout greater than one is not supported yet")
+        f, q2 = hits[0]
+        if q2 in vis:
+            return None
+        vis.add(q2)
+        atom = ("f",) if f == "copy" else ("c", tuple(f[1]))
+        return ("tip", (atom,), q2)
+
+    return _reduce(_bind(tree, k))
+
+
+def _abstract(tree):
+    """Name every node by its path; returns (kappa list, abstract tree)
+    (Determinization.hs:165-183)."""
+    kappa = []
+
+    def go(v, t):
+        kappa.append((v, t[1]))
+        if t[0] == "tip":
+            return ("tip", v, t[2])
+        return ("fork", v, tuple(go(v + (m,), c) for m, c in enumerate(t[2])))
+
+    at = go((), tree)
+    return kappa, at
+
+
+def _unabstract_outputs(tree):
+    if tree[0] == "tip":
+        return ("tip", (("v", tree[1]),), tree[2])
+    return ("fork", (("v", tree[1]),), tuple(_unabstract_outputs(c) for c in tree[2]))
+
+
+def normalize_update(atoms):
+    """normalizeUpdateStringFunc (SymbolicSST.hs:107-115)."""
+    out = []
+    for a in atoms:
+        if a[0] == "c":
+            if not a[1]:
+                continue
+            if out and out[-1][0] == "c":
+                out[-1] = ("c", out[-1][1] + a[1])
+                continue
+        out.append(a)
+    return tuple(out)
+
+
+class SST:
+    """states: 0..n-1; edges[q] = [(byteset, {var: atoms}, q')];
+    final[q] = atoms (only "v"/"c"); variables are ints with 0 = output
+    register, numbered in tree pre-order (`enumerateVariables`,
+    SymbolicSST.hs:346-367)."""
+
+    def __init__(self, nstates, edges, initial, final, nvars):
+        self.nstates = nstates
+        self.edges = edges
+        self.initial = initial
+        self.final = final
+        self.nvars = nvars
+
+    def variables(self):
+        vs = set()
+        for es in self.edges.values():
+            for _, upd, _ in es:
+                vs.update(upd.keys())
+        for atoms in self.final.values():
+            vs.update(a[1] for a in atoms if a[0] == "v")
+        return vs
+
+
+def sst_from_fst(fst, max_states=200000):
+    """sstFromFST in singleton mode (Determinization.hs:231-257)."""
+    if fst.has_actions():
+        raise ValueError("Transducer contains action symbols - direct SST generation not supported")
+    init = ("tip", (), fst.initial)
+    index = {init: 0}
+    order = [init]
+    trans = []
+    finals = {}
+    i = 0
+    while i < len(order):
+        t = order[i]
+        i += 1
+        tcl = _closure(fst, _unabstract_outputs(t))
+        fin = _eof(fst, tcl)
+        if fin is not None and fin[0] == "tip":
+            finals[t] = normalize_update(fin[1])
+        if tcl is None:
+            continue
+        for p in coarsest_predicate_set(fst, _tflat(tcl)):
+            tr = _closure(fst, _consume(fst, p, _closure(fst, tcl)))
+            if tr is None:
+                continue
+            kappa, t2 = _abstract(tr)
+            if BS.size(p) == 1:
+                b = BS.to_list(p)[0]
+                kappa = [(v, tuple(("c", (b,)) if a == ("f",) else a for a in w)) for v, w in kappa]
+            upd = {}
+            for v, w in kappa:
+                assert v not in upd, "Inconsistent register update"
+                upd[v] = normalize_update(w)
+            if t2 not in index:
+                if len(order) >= max_states:
+                    raise MemoryError("SST exceeds %d states" % max_states)
+                index[t2] = len(order)
+                order.append(t2)
+            trans.append((t, p, upd, t2))
+    # enumerate variables in tuple (pre-order) order
+    vs = {()}
+    for _, _, upd, _ in trans:
+        vs.update(upd.keys())
+        for w in upd.values():
+            vs.update(a[1] for a in w if a[0] == "v")
+    for w in finals.values():
+        vs.update(a[1] for a in w if a[0] == "v")
+    vid = {v: k for k, v in enumerate(sorted(vs))}
+
+    def ren(w):
+        return tuple(("v", vid[a[1]]) if a[0] == "v" else a for a in w)
+
+    edges = {}
+    for t, p, upd, t2 in trans:
+        edges.setdefault(index[t], []).append(
+            (p, {vid[v]: ren(w) for v, w in upd.items()}, index[t2]))
+    final = {index[t]: ren(w) for t, w in finals.items()}
+    return SST(len(order), edges, 0, final, len(vid))
+
+
+# ------------------------------------------------------------- optimisation
+_AMB = "amb"
+
+
+def _lift(rho, atoms):
+    """liftAbstractValuation (SymbolicSST.hs:208-219): None if some variable
+    has no abstract value yet."""
+    acc = ()
+    amb = False
+    for a in atoms:
+        if a[0] == "v":
+            if a[1] not in rho:
+                return None
+            v = rho[a[1]]
+            if v == _AMB:
+                amb = True
+            else:
+                acc = acc + v
+        elif a[0] == "f":
+            amb = True
+        else:
+            acc = acc + a[1]
+    return _AMB if amb else acc
+
+
+def _lub(a, b):
+    if a == _AMB or b == _AMB or a != b:
+        return _AMB
+    return a
+
+
+def optimize(sst, level=3):
+    """Constant propagation of registers (`optimize`, SymbolicSST.hs:323-331;
+    abstract interpretation :273-321).  level 0 = off; 1-2 = weak variant
+    (a register that reads itself is ambiguous); 3 = full."""
+    if level <= 0:
+        return sst
+    weak = level < 3
+    gamma = {q: {} for q in range(sst.nstates)}
+    states = set(range(sst.nstates))
+    while states:
+        acc = {}
+        for r in states:
+            rho_r = gamma[r]
+            for _, kappa, s in sst.edges.get(r, ()):
+                new = dict(rho_r)
+                for k, usf in kappa.items():
+                    if weak:
+                        tmp = dict(rho_r)
+                        tmp[k] = _AMB
+                        val = _lift(tmp, usf)
+                    else:
+                        val = _lift(rho_r, usf)
+                    if val is not None:
+                        new[k] = val
+                if s in acc:
+                    old = acc[s]
+                    for k, v in new.items():
+                        old[k] = _lub(old[k], v) if k in old else v
+                else:
+                    acc[s] = new
+        nxt = set()
+        for s, rho2 in acc.items():
+            rho_s = gamma[s]
+            if all(k in rho_s and (rho_s[k] == _AMB or rho_s[k] == v) for k, v in rho2.items()):
+                continue
+            merged = dict(rho_s)
+            for k, v in rho2.items():
+                merged[k] = _lub(merged[k], v) if k in merged else v
+            gamma[s] = merged
+            nxt.add(s)
+        states = nxt
+
+    def apply(rho, atoms):
+        return normalize_update(tuple(
+            ("c", rho[a[1]]) if a[0] == "v" and a[1] in rho and rho[a[1]] != _AMB else a
+            for a in atoms))
+
+    edges = {}
+    for q, es in sst.edges.items():
+        new = []
+        for p, kappa, q2 in es:
+            exact = {k for k, v in gamma[q2].items() if v != _AMB}
+            new.append((p, {k: apply(gamma[q], w) for k, w in kappa.items() if k not in exact}, q2))
+        edges[q] = new
+    final = {q: apply(gamma[q], w) for q, w in sst.final.items()}
+    return SST(sst.nstates, edges, sst.initial, final, sst.nvars)
+
+
+# ---------------------------------------------------------------- simulator
+def run_sst(sst, data: bytes):
+    """Sequential SST semantics with *persistent* registers, i.e. what the
+    emitted C program computes (registers absent from an update keep their
+    value).  Returns (accepted, output, consumed)."""
+    regs = {v: b"" for v in range(sst.nvars)}
+    out = bytearray()
+    q = sst.initial
+    for i, b in enumerate(data):
+        hit = None
+        for p, upd, q2 in sst.edges.get(q, ()):
+            if (p >> b) & 1:
+                hit = (upd, q2)
+                break
+        if hit is None:
+            return False, bytes(out), i
+        upd, q = hit
+        new = {}
+        for v, atoms in upd.items():
+            buf = bytearray()
+            for a in atoms:
+                if a[0] == "v":
+                    buf += regs[a[1]]
+                elif a[0] == "c":
+                    buf += bytes(a[1])
+                else:
+                    buf.append(b)
+            new[v] = bytes(buf)
+        regs.update(new)
+        out += regs[0]
+        regs[0] = b""
+    if q not in sst.final:
+        return False, bytes(out), len(data)
+    for a in sst.final[q]:
+        out += regs[a[1]] if a[0] == "v" else bytes(a[1])
+    return True, bytes(out), len(data)
