@@ -1,0 +1,125 @@
+/*
+ * kexcuda.h -- C ABI of libkexcuda.so, the B200 (sm_100a) execution back end
+ * for compiled Kleenex streaming string transducers.
+ *
+ * The reference has no FFI for this path: the seam is the generated-code <->
+ * runtime ABI of crt/crt.c:103-105 (`void printCompilationInfo(); void init();
+ * void match(int phase);`) plus the process contract of the compiled binary
+ * (crt/crt.c:372-467: stdin -> stdout, exit 0 on accept, exit 1 and
+ * "Match error at input symbol <count>!" on reject).  The entry points below
+ * are what a `KMC.Program.Backends.CUDA` module (the sibling of
+ * src/KMC/Program/Backends/C.hs:529-540 `compileProgram`) would bind instead
+ * of piping C text to `cc`: it serialises the pipeline's tables into a
+ * `kexprog` blob (kleenexlang_b200/kexprog.py documents the layout) and the
+ * launcher hands the blob and the input bytes to this library.
+ *
+ * Plain pointers and sizes only.  All functions return KEX_OK (0) or a
+ * negative KEX_ERR_* code; nothing is printed and nothing calls exit().
+ */
+#ifndef KEXCUDA_H
+#define KEXCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KEX_OK               0
+#define KEX_ERR_BAD_BLOB    -1   /* blob magic/version/offsets invalid            */
+#define KEX_ERR_CUDA        -2   /* a CUDA runtime call failed (kex_last_cuda_error) */
+#define KEX_ERR_OUT_CAP     -3   /* output buffer too small; *out_len = bytes needed */
+#define KEX_ERR_UNSUPPORTED -4   /* program exceeds a device-table limit          */
+#define KEX_ERR_ARG         -5   /* bad argument (null, misaligned input, phase)  */
+
+/* Match status, mirroring the exit status of the reference binary
+ * (src/KMC/Program/Backends/C.hs:79-81). */
+#define KEX_ACCEPT 0
+#define KEX_REJECT 1
+
+typedef struct kex_program kex_program;
+
+typedef struct {
+  uint32_t nphases;        /* NUM_PHASES of the pipeline (C.hs:41)               */
+  uint32_t nstates;        /* SST states of phase 0                              */
+  uint32_t nclasses;       /* byte classes of phase 0                            */
+  uint32_t nregs;          /* registers incl. the output stream, phase 0         */
+  uint32_t nactions;       /* distinct register-update actions, phase 0          */
+  uint32_t max_out_per_byte; /* worst-case output bytes per input byte, phase 0  */
+  uint32_t chunk_bytes;    /* bytes one device chunk covers                      */
+  uint32_t reserved;
+} kex_info_t;
+
+/* Replaces the emit+cc step of compileProgram (C.hs:529-568) and `init()`
+ * (C.hs:470-484): parse a kexprog blob and upload its tables to `device`. */
+int kex_load(const void *blob, size_t blob_len, int device, kex_program **out);
+
+/* Replaces process teardown; frees tables and scratch. */
+void kex_free(kex_program *p);
+
+/* Replaces `-i` / printCompilationInfo (crt/crt.c:384-386, C.hs:49-52). */
+int kex_info(const kex_program *p, uint32_t phase, kex_info_t *info);
+
+/* Replaces `run(phase)` for every phase of the pipeline (crt/crt.c:356-364,
+ * 414-455) with input and output resident in device memory.  `d_in` must be
+ * 16-byte aligned.  On KEX_OK: *status is KEX_ACCEPT or KEX_REJECT, *out_len
+ * the bytes written to d_out, *fail_count the reference's `count` (bytes
+ * consumed by completed transitions, C.hs:79-81) when rejecting.  A rejecting
+ * run leaves exactly the whole 16 KiB flushes the C runtime would have
+ * written (crt/crt.c:107-159,217-227).  `stream` is a cudaStream_t or NULL. */
+int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n,
+                   uint8_t *d_out, size_t out_cap, size_t *out_len,
+                   int *status, size_t *fail_count, void *stream);
+
+/* Same, with host buffers: host->device copy of the input, the run, and a
+ * device->host copy of the output all happen inside the call
+ * (the stdin/stdout role of crt/crt.c:293-312,107-136). */
+int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n,
+                 uint8_t *h_out, size_t out_cap, size_t *out_len,
+                 int *status, size_t *fail_count);
+
+/* ---- sharded evaluation (one shard per GPU; single-phase programs) --------
+ * The transducer run is a prefix computation over (state map, register fate
+ * map).  A shard is evaluated in three steps so that ranks can exchange the
+ * two small summaries (all-gather) between them:
+ *
+ *   kex_shard_summarize : state map of the shard for every start state
+ *   kex_shard_walk      : given the true start state -> end state, first
+ *                         failure, fate map of the registers over the shard
+ *   kex_shard_emit      : given which registers are live at the shard's end
+ *                         -> write the shard's output bytes
+ *
+ * State maps have nstates+1 uint16 entries (the last is the FAIL sink), fate
+ * maps nregs uint8 entries (0 = flushed to the stream, 0xFF = dropped).     */
+int kex_shard_summarize(kex_program *p, const uint8_t *d_in, size_t n,
+                        uint16_t *h_state_map, void *stream);
+int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *end_state,
+                   size_t *fail_pos /* (size_t)-1 if none */, uint8_t *h_fate_map,
+                   void *stream);
+int kex_shard_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff,
+                   uint8_t *d_out, size_t out_cap, size_t *out_len, void *stream);
+
+/* Final-state action: is `state` accepting, which registers does the end-of-
+ * input action flush (bit r), and its literal tail (SSTCompiler.hs:147-154). */
+int kex_final_action(const kex_program *p, uint32_t state, int *accepting,
+                     uint32_t *flush_mask, const uint8_t **tail, size_t *tail_len);
+
+/* Upper bound on the output size for n input bytes (all phases). */
+size_t kex_out_bound(const kex_program *p, size_t n);
+
+/* Kernel launches issued by the most recent kex_run_* / kex_shard_* call. */
+uint32_t kex_last_launch_count(const kex_program *p);
+
+/* Duration in ms of the dominant (emit) kernel in the most recent run, timed
+ * with CUDA events on the launching stream; 0 if timing is disabled. */
+int kex_set_timing(kex_program *p, int enabled);
+float kex_last_kernel_ms(const kex_program *p, uint32_t which);
+
+const char *kex_strerror(int code);
+const char *kex_last_cuda_error(const kex_program *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEXCUDA_H */

@@ -1,0 +1,1205 @@
+// kexcuda.cu -- B200 (sm_100a) execution back end for compiled Kleenex
+// streaming string transducers.  C ABI in include/kexcuda.h.
+//
+// What the reference does sequentially (one goto-threaded `matchN()` per
+// phase, src/KMC/Program/Backends/C.hs:72-83, over the buffered runtime
+// crt/crt.c) is evaluated here as a prefix computation over the SST's
+// transition monoid (src/KMC/SymbolicSST.hs:122-136):
+//
+//   k_chunk_maps   K1  per 4 KiB chunk: state map Q -> Q, speculating over all
+//                      start states with converging tracks   (readnext/consume
+//                      + the state chain of matchN, run for every start state)
+//   k_compose /    K2  hierarchical composition of the maps and push-down of
+//   k_push_states      the true start state of every chunk  (the sequential
+//                      dependence between crt.c's 16 KiB windows)
+//   k_true_walk    K3  per chunk from its true start state: state samples
+//                      every 32 B, first failing position (C.hs:79-81),
+//                      register fate map / resolved + pending byte counts
+//                      (crt.c:161-259 append/concat/reset, counted not copied)
+//   k_compose /    K4  backward composition of the fate maps: which registers
+//   k_push_live        at a chunk's end still reach the stream; output offsets
+//   k_emit         K5  per chunk: decide per created byte whether it survives,
+//                      then write it at its final offset (outputconst /
+//                      outputarray / output, crt.c:217-283) through a shared-
+//                      memory staging window and 16-byte coalesced stores
+//
+// The chunk that creates a byte writes it; registers never move data.
+// Integer/byte work only: no tensor cores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/kexcuda.h"
+
+#define KEX_CHUNK 4096u          // bytes per chunk (K1/K3 thread, K5 CTA)
+#define KEX_SUB 32u              // bytes per K5 thread
+#define KEX_NT (KEX_CHUNK / KEX_SUB)   // K5 threads per CTA (128)
+#define KEX_FANIN 64u            // maps composed per group per level
+#define KEX_TRACKS 8             // speculative tracks kept in registers (K1)
+#define KEX_STAGE 20480u         // K5 staging window bytes
+#define KEX_DEAD 0xFFu
+#define KEX_NONE32 0xFFFFFFFFu
+#define KEX_NONE64 0xFFFFFFFFFFFFFFFFull
+
+enum { KIND_NOP = 0, KIND_OUTSYM = 1, KIND_OUTONLY = 2, KIND_GENERAL = 3 };
+enum { PIECE_CONST = 0, PIECE_SYM = 1 };
+
+struct ActHdr { uint32_t kind, npieces, piece_off, outlen0, flush_mask, total_len; };
+struct Piece { uint8_t target, kind; uint16_t len; uint32_t off; };
+
+struct PhaseDev {
+  uint32_t Q, C, R, A, init, max_out;
+  const uint8_t *cls;        // [256]
+  const uint32_t *trans;     // [(Q+1)*C]  next | action << 16
+  const uint16_t *nextpm;    // [(Q+1)*C]  next state pre-multiplied by C
+  const ActHdr *acts;        // [A]
+  const uint32_t *actinfo;   // [A] kind | outlen0 << 8
+  const uint8_t *fate;       // [A*R]
+  const uint32_t *addlen;    // [A*R]
+  const Piece *pieces;
+  const uint8_t *consts;
+  const uint32_t *img_cnt;   // [C]   distinct non-FAIL successors per class
+  const uint16_t *img_state; // [C*Q] those successors (pre-multiplied by C)
+  const uint16_t *img_idx;   // [C*(Q+1)] start state -> track index or 0xFFFF
+};
+
+struct RunResult {               // device -> host summary of a walk
+  unsigned long long fail_pos;
+  unsigned long long total_out;
+  uint32_t end_state;
+  uint32_t pad;
+};
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint4 &v, int j) {
+  uint32_t w = (j < 4) ? v.x : (j < 8) ? v.y : (j < 12) ? v.z : v.w;
+  return (w >> ((j & 3) * 8)) & 0xFFu;
+}
+
+// ------------------------------------------------------------------- K1
+// One thread per chunk.  Track t follows the t-th distinct successor of the
+// chunk's first byte; tracks that meet stay together, so the loop collapses
+// to a single dependent lookup per byte once they have converged.
+__global__ void __launch_bounds__(128)
+k_chunk_maps(PhaseDev P, const uint8_t *__restrict__ in, size_t n, size_t nchunks,
+             uint16_t *__restrict__ maps) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t *cls = smem;
+  uint16_t *nxt = (uint16_t *)(smem + 256);
+  const uint32_t Q1 = P.Q + 1, C = P.C;
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cls[i] = P.cls[i];
+  for (uint32_t i = threadIdx.x; i < Q1 * C; i += blockDim.x) nxt[i] = P.nextpm[i];
+  __syncthreads();
+  size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= nchunks) return;
+  const size_t base = chunk * KEX_CHUNK;
+  const uint32_t len = (uint32_t)((n - base < KEX_CHUNK) ? (n - base) : KEX_CHUNK);
+  const uint32_t FAILPM = P.Q * C;
+  uint16_t *row = maps + chunk * Q1;
+  const uint8_t *p = in + base;
+  const uint32_t nwords = (len + 15u) >> 4;
+  uint4 w0 = ld_stream16(p);
+  const uint32_t c0 = cls[w0.x & 0xFFu];
+  const uint32_t m = P.img_cnt[c0];
+  const uint16_t *ist = P.img_state + (size_t)c0 * P.Q;
+  const uint16_t *iidx = P.img_idx + (size_t)c0 * Q1;
+  for (uint32_t q = 0; q < Q1; ++q) row[q] = (uint16_t)P.Q;
+  for (uint32_t tb = 0; tb < m; tb += KEX_TRACKS) {
+    uint32_t s[KEX_TRACKS];
+#pragma unroll
+    for (int t = 0; t < KEX_TRACKS; ++t) s[t] = (tb + t < m) ? ist[tb + t] : FAILPM;
+    bool single = false;
+    uint32_t alive = 0, s0 = FAILPM;
+    for (uint32_t w = 0; w < nwords; ++w) {
+      uint4 v = (w == 0) ? w0 : ld_stream16(p + 16u * w);
+      const uint32_t lim = (len - 16u * w < 16u) ? (len - 16u * w) : 16u;
+      if (single) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if ((w == 0 && j == 0) || (uint32_t)j >= lim) continue;
+          s0 = nxt[s0 + cls[byte_of(v, j)]];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if ((w == 0 && j == 0) || (uint32_t)j >= lim) continue;
+          const uint32_t c = cls[byte_of(v, j)];
+#pragma unroll
+          for (int t = 0; t < KEX_TRACKS; ++t) s[t] = nxt[s[t] + c];
+        }
+        // converged?  all live tracks in one state
+        uint32_t v0 = FAILPM;
+        bool conv = true;
+#pragma unroll
+        for (int t = 0; t < KEX_TRACKS; ++t) {
+          if (s[t] != FAILPM) {
+            if (v0 == FAILPM) v0 = s[t];
+            else if (s[t] != v0) conv = false;
+          }
+        }
+        if (conv) {
+          single = true;
+          s0 = v0;
+          alive = 0;
+#pragma unroll
+          for (int t = 0; t < KEX_TRACKS; ++t) if (s[t] != FAILPM) alive |= 1u << t;
+          if (v0 == FAILPM) break;   // every track of this batch is dead
+        }
+      }
+    }
+    if (single) {
+#pragma unroll
+      for (int t = 0; t < KEX_TRACKS; ++t) s[t] = ((alive >> t) & 1u) ? s0 : FAILPM;
+    }
+    for (uint32_t q = 0; q < P.Q; ++q) {
+      const uint32_t ix = iidx[q];
+      if (ix >= tb && ix < tb + KEX_TRACKS) {
+        uint32_t r = FAILPM;
+#pragma unroll
+        for (int t = 0; t < KEX_TRACKS; ++t) if (ix - tb == (uint32_t)t) r = s[t];
+        row[q] = (uint16_t)(r / C);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------- K2 / K4 scans
+// parent[g] = child[g*G] ; child[g*G+1] ; ...   (apply left to right).
+// FATE maps have absorbing values 0 (flushed) and 0xFF (dropped).
+template <typename T, bool FATE>
+__global__ void k_compose(const T *__restrict__ child, size_t nchild, T *__restrict__ parent,
+                          uint32_t D) {
+  const size_t g = blockIdx.x;
+  const size_t lo = g * KEX_FANIN;
+  const size_t hi = (lo + KEX_FANIN < nchild) ? (lo + KEX_FANIN) : nchild;
+  for (uint32_t q = threadIdx.x; q < D; q += blockDim.x) {
+    uint32_t s = q;
+    for (size_t j = lo; j < hi; ++j) {
+      if (FATE && (s == 0u || s == KEX_DEAD)) break;
+      s = child[j * D + s];
+    }
+    parent[g * D + q] = (T)s;
+  }
+}
+
+__global__ void k_push_states(const uint16_t *__restrict__ child_maps, size_t nchild,
+                              const uint16_t *__restrict__ parent_start, size_t nparent,
+                              uint16_t *__restrict__ child_start, uint32_t D) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nparent) return;
+  const size_t lo = g * KEX_FANIN;
+  const size_t hi = (lo + KEX_FANIN < nchild) ? (lo + KEX_FANIN) : nchild;
+  uint32_t s = parent_start[g];
+  for (size_t j = lo; j < hi; ++j) {
+    child_start[j] = (uint16_t)s;
+    s = child_maps[j * D + s];
+  }
+}
+
+__device__ __forceinline__ uint32_t pullback(const uint8_t *__restrict__ F, uint32_t R, uint32_t L) {
+  // registers whose content goes (through F) to the stream or to a live register
+  const uint32_t m = L | 1u;
+  uint32_t r = 0;
+  for (uint32_t i = 1; i < R; ++i) {
+    const uint32_t d = F[i];
+    if (d != KEX_DEAD && ((m >> d) & 1u)) r |= 1u << i;
+  }
+  return r;
+}
+
+__global__ void k_push_live(const uint8_t *__restrict__ child_fate, size_t nchild,
+                            const uint32_t *__restrict__ parent_live, size_t nparent,
+                            uint32_t *__restrict__ child_live, uint32_t R) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nparent) return;
+  const size_t lo = g * KEX_FANIN;
+  const size_t hi = (lo + KEX_FANIN < nchild) ? (lo + KEX_FANIN) : nchild;
+  uint32_t L = parent_live[g];
+  for (size_t j = hi; j-- > lo;) {
+    child_live[j] = L;
+    L = pullback(child_fate + j * R, R, L);
+  }
+}
+
+__global__ void k_set_u16(uint16_t *p, uint32_t v) { *p = (uint16_t)v; }
+__global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+
+// ------------------------------------------------------------------- K3
+__global__ void __launch_bounds__(128)
+k_true_walk(PhaseDev P, const uint8_t *__restrict__ in, size_t n, size_t nchunks,
+            const uint16_t *__restrict__ start, uint16_t *__restrict__ samples,
+            uint8_t *__restrict__ chunk_fate, uint32_t *__restrict__ chunk_pend,
+            unsigned long long *__restrict__ chunk_resolved, uint32_t *__restrict__ chunk_fail,
+            RunResult *__restrict__ res) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t *cls = smem;
+  const uint32_t Q1 = P.Q + 1, C = P.C, R = P.R;
+  uint32_t *trans = (uint32_t *)(smem + 256);
+  uint32_t *actinfo = trans + Q1 * C;
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cls[i] = P.cls[i];
+  for (uint32_t i = threadIdx.x; i < Q1 * C; i += blockDim.x) trans[i] = P.trans[i];
+  for (uint32_t i = threadIdx.x; i < P.A; i += blockDim.x) actinfo[i] = P.actinfo[i];
+  __syncthreads();
+  size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= nchunks) return;
+  const size_t base = chunk * KEX_CHUNK;
+  const uint32_t len = (uint32_t)((n - base < KEX_CHUNK) ? (n - base) : KEX_CHUNK);
+  const uint8_t *p = in + base;
+  uint32_t s = start[chunk];
+  uint8_t F[32];
+  uint32_t ln[32];
+  for (uint32_t r = 0; r < R; ++r) { F[r] = (uint8_t)r; ln[r] = 0; }
+  unsigned long long resolved = 0;
+  uint32_t fail = KEX_NONE32;
+  uint16_t *srow = samples + chunk * KEX_NT;
+  const uint32_t nwords = (len + 15u) >> 4;
+  uint32_t pk[4] = {0, 0, 0, 0};
+  uint32_t nrec = 0;   // samples recorded so far
+  for (uint32_t w = 0; w < nwords && fail == KEX_NONE32; ++w) {
+    uint4 v = ld_stream16(p + 16u * w);
+    const uint32_t lim = (len - 16u * w < 16u) ? (len - 16u * w) : 16u;
+    if ((w & 1u) == 0) {   // a 32-byte sub-chunk starts here
+      const uint32_t slot = nrec & 7u;
+      if (slot & 1u) pk[slot >> 1] |= s << 16; else pk[slot >> 1] = s;
+      ++nrec;
+      if (slot == 7u) *(uint4 *)(srow + (nrec - 8u)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if ((uint32_t)j >= lim || fail != KEX_NONE32) continue;
+      const uint32_t e = trans[s * C + cls[byte_of(v, j)]];
+      const uint32_t ns = e & 0xFFFFu, a = e >> 16;
+      if (ns == P.Q) { fail = 16u * w + j; continue; }
+      s = ns;
+      const uint32_t info = actinfo[a];
+      if ((info & 0xFFu) != KIND_GENERAL) {
+        resolved += info >> 8;
+      } else {
+        const uint8_t *fa = P.fate + (size_t)a * R;
+        const uint32_t *al = P.addlen + (size_t)a * R;
+        uint32_t nl[32];
+        for (uint32_t r = 0; r < R; ++r) nl[r] = al[r];
+        for (uint32_t r = 1; r < R; ++r) {
+          const uint32_t d = fa[r];
+          if (d == 0u) resolved += ln[r];
+          else if (d != KEX_DEAD) nl[d] += ln[r];
+        }
+        resolved += nl[0];
+        for (uint32_t r = 1; r < R; ++r) ln[r] = nl[r];
+        for (uint32_t r = 1; r < R; ++r) {
+          const uint32_t x = F[r];
+          if (x != 0u && x != KEX_DEAD) F[r] = fa[x];
+        }
+      }
+    }
+  }
+  for (uint32_t k = nrec & ~7u; k < nrec; ++k) {   // partially filled sample pack
+    const uint32_t slot = k & 7u;
+    srow[k] = (uint16_t)((slot & 1u) ? (pk[slot >> 1] >> 16) : (pk[slot >> 1] & 0xFFFFu));
+  }
+  chunk_fail[chunk] = fail;
+  chunk_resolved[chunk] = resolved;
+  if (R > 1) {
+    for (uint32_t r = 0; r < R; ++r) {
+      chunk_fate[chunk * R + r] = F[r];
+      chunk_pend[chunk * R + r] = ln[r];
+    }
+  }
+  if (chunk == nchunks - 1) res->end_state = (fail == KEX_NONE32) ? s : P.Q;
+}
+
+__global__ void k_reduce_fail(const uint32_t *__restrict__ chunk_fail, size_t nchunks,
+                              RunResult *__restrict__ res) {
+  __shared__ unsigned long long best[32];
+  unsigned long long m = KEX_NONE64;
+  for (size_t i = threadIdx.x; i < nchunks; i += blockDim.x) {
+    const uint32_t f = chunk_fail[i];
+    if (f != KEX_NONE32) {
+      const unsigned long long pos = (unsigned long long)i * KEX_CHUNK + f;
+      if (pos < m) m = pos;
+      break;   // later chunks of this thread are further right
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long x = __shfl_xor_sync(0xFFFFFFFFu, m, o);
+    if (x < m) m = x;
+  }
+  if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t w = 1; w < (blockDim.x >> 5); ++w) if (best[w] < m) m = best[w];
+    res->fail_pos = m;
+  }
+}
+
+// -------------------------------------------------- output lengths & offsets
+__global__ void k_outlen(const uint32_t *__restrict__ pend, const unsigned long long *__restrict__ resolved,
+                         const uint32_t *__restrict__ live, size_t nchunks, uint32_t R,
+                         unsigned long long *__restrict__ outlen) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nchunks) return;
+  unsigned long long t = resolved[i];
+  if (R > 1) {
+    const uint32_t L = live[i];
+    for (uint32_t r = 1; r < R; ++r) if ((L >> r) & 1u) t += pend[i * R + r];
+  }
+  outlen[i] = t;
+}
+
+#define SCAN_ITEMS 8
+#define SCAN_THREADS 256
+#define SCAN_TILE (SCAN_ITEMS * SCAN_THREADS)
+
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long *total,
+                                                              unsigned long long *sh) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) sh[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = (lane < (blockDim.x >> 5)) ? sh[lane] : 0ull;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+      if (lane >= (uint32_t)o) w += y;
+    }
+    sh[32 + lane] = w;   // inclusive warp totals
+  }
+  __syncthreads();
+  const unsigned long long wbase = warp ? sh[32 + warp - 1] : 0ull;
+  *total = sh[32 + (blockDim.x >> 5) - 1];
+  const unsigned long long r = wbase + x - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_sums(const unsigned long long *__restrict__ v, size_t n, unsigned long long *__restrict__ bsum) {
+  __shared__ unsigned long long sh[64];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  unsigned long long t = 0;
+  for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) t += v[base + k];
+  unsigned long long total;
+  block_excl_scan(t, &total, sh);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_top(unsigned long long *__restrict__ bsum, size_t nb, RunResult *__restrict__ res) {
+  __shared__ unsigned long long sh[64];
+  unsigned long long carry = 0;
+  for (size_t base = 0; base < nb; base += SCAN_THREADS) {
+    const size_t i = base + threadIdx.x;
+    const unsigned long long v = (i < nb) ? bsum[i] : 0ull;
+    unsigned long long total;
+    const unsigned long long e = block_excl_scan(v, &total, sh);
+    if (i < nb) bsum[i] = carry + e;
+    carry += total;
+  }
+  if (threadIdx.x == 0) res->total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_apply(const unsigned long long *__restrict__ v, size_t n, const unsigned long long *__restrict__ bsum,
+             unsigned long long *__restrict__ off) {
+  __shared__ unsigned long long sh[64];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  unsigned long long loc[SCAN_ITEMS];
+  unsigned long long t = 0;
+  for (int k = 0; k < SCAN_ITEMS; ++k) { loc[k] = (base + k < n) ? v[base + k] : 0ull; t += loc[k]; }
+  unsigned long long total;
+  unsigned long long e = block_excl_scan(t, &total, sh) + bsum[blockIdx.x];
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) off[base + k] = e;
+    e += loc[k];
+  }
+}
+
+// ------------------------------------------------------------------- K5
+// One CTA per chunk, one thread per 32-byte sub-chunk.
+//   pass A  forward from the sampled state: action id per position, bytes that
+//           certainly reach the stream, fate map of the sub-chunk
+//   scan    suffix composition of the sub-chunk fate maps -> live registers at
+//           each sub-chunk's end (only if some position moves registers)
+//   pass B  backward: survival mask per register-moving position, byte count
+//   pass C  forward: write surviving bytes at their final offsets
+// MB = bytes of a survival mask kept per position (0: program has no registers)
+template <int MB>
+__global__ void __launch_bounds__(KEX_NT)
+k_emit(PhaseDev P, const uint8_t *__restrict__ in, size_t n_eff,
+       const uint16_t *__restrict__ samples, const unsigned long long *__restrict__ outoff,
+       const uint32_t *__restrict__ live_end, uint8_t *__restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t Q1 = P.Q + 1, C = P.C, R = P.R;
+  const uint32_t tid = threadIdx.x;
+  // ---- carve shared memory
+  uint8_t *in_sm = smem;                                   // KEX_CHUNK
+  uint8_t *stage = in_sm + KEX_CHUNK;                      // KEX_STAGE + 32
+  uint16_t *act_sm = (uint16_t *)(stage + KEX_STAGE + 32); // KEX_CHUNK entries, [j][tid]
+  uint8_t *mask_sm = (uint8_t *)(act_sm + KEX_CHUNK);      // KEX_CHUNK * MB
+  uint8_t *maps_sm = mask_sm + (size_t)KEX_CHUNK * MB;     // 2 * KEX_NT * R   (MB > 0)
+  uint8_t *tbl = maps_sm + (MB ? 2u * KEX_NT * 32u : 0u);
+  uint32_t *trans = (uint32_t *)tbl;
+  uint32_t *actinfo = trans + Q1 * C;
+  uint8_t *cls = (uint8_t *)(actinfo + P.A);
+  __shared__ uint32_t warp_sums[KEX_NT / 32];
+  __shared__ uint32_t tile_total;
+
+  for (uint32_t i = tid; i < Q1 * C; i += KEX_NT) trans[i] = P.trans[i];
+  for (uint32_t i = tid; i < P.A; i += KEX_NT) actinfo[i] = P.actinfo[i];
+  for (uint32_t i = tid; i < 256; i += KEX_NT) cls[i] = P.cls[i];
+
+  const size_t tile = blockIdx.x;
+  const size_t base = tile * KEX_CHUNK;
+  const uint32_t tlen = (uint32_t)((n_eff - base < KEX_CHUNK) ? (n_eff - base) : KEX_CHUNK);
+  {
+    const uint32_t nw = (tlen + 15u) >> 4;
+    for (uint32_t w = tid; w < nw; w += KEX_NT)
+      *(uint4 *)(in_sm + 16u * w) = ld_stream16(in + base + 16u * w);
+  }
+  __syncthreads();
+
+  // ---- pass A
+  const uint32_t lo = tid * KEX_SUB;
+  const uint32_t cnt_pos = (lo < tlen) ? ((tlen - lo < KEX_SUB) ? (tlen - lo) : KEX_SUB) : 0u;
+  uint32_t s = cnt_pos ? samples[tile * KEX_NT + tid] : 0u;
+  uint32_t cnt = 0;
+  bool anygen = false;
+  uint8_t f[32];
+  if (MB) for (uint32_t r = 0; r < R; ++r) f[r] = (uint8_t)r;
+  for (uint32_t j = 0; j < cnt_pos; ++j) {
+    const uint32_t e = trans[s * C + cls[in_sm[lo + j]]];
+    const uint32_t a = e >> 16;
+    s = e & 0xFFFFu;
+    act_sm[j * KEX_NT + tid] = (uint16_t)a;
+    const uint32_t info = actinfo[a];
+    if (!MB || (info & 0xFFu) != KIND_GENERAL) {
+      cnt += info >> 8;
+    } else {
+      anygen = true;
+      const uint8_t *fa = P.fate + (size_t)a * R;
+      for (uint32_t r = 1; r < R; ++r) {
+        const uint32_t x = f[r];
+        if (x != 0u && x != KEX_DEAD) f[r] = fa[x];
+      }
+    }
+  }
+
+  if (MB) {
+    const int any = __syncthreads_or(anygen ? 1 : 0);
+    if (any) {
+      // ---- suffix composition of the sub-chunk fate maps (Hillis-Steele)
+      uint8_t *cur = maps_sm, *nxt = maps_sm + KEX_NT * R;
+      for (uint32_t r = 0; r < R; ++r) cur[tid * R + r] = f[r];
+      __syncthreads();
+      for (uint32_t d = 1; d < KEX_NT; d <<= 1) {
+        for (uint32_t r = 0; r < R; ++r) {
+          uint32_t x = cur[tid * R + r];
+          if (tid + d < KEX_NT && x != 0u && x != KEX_DEAD) x = cur[(tid + d) * R + x];
+          nxt[tid * R + r] = (uint8_t)x;
+        }
+        __syncthreads();
+        uint8_t *t = cur; cur = nxt; nxt = t;
+      }
+      // ---- pass B
+      if (anygen) {
+        const uint32_t Lt = live_end[tile];
+        uint32_t L = (tid == KEX_NT - 1) ? Lt : pullback(cur + (tid + 1) * R, R, Lt);
+        for (uint32_t j = cnt_pos; j-- > 0;) {
+          const uint32_t a = act_sm[j * KEX_NT + tid];
+          if ((actinfo[a] & 0xFFu) != KIND_GENERAL) continue;
+          const uint32_t m = L | 1u;
+          if (MB == 1) mask_sm[j * KEX_NT + tid] = (uint8_t)m;
+          else ((uint32_t *)mask_sm)[j * KEX_NT + tid] = m;
+          const uint8_t *fa = P.fate + (size_t)a * R;
+          const uint32_t *al = P.addlen + (size_t)a * R;
+          uint32_t nl = 0;
+          for (uint32_t r = 0; r < R; ++r) {
+            if ((m >> r) & 1u) cnt += al[r];
+            const uint32_t d = fa[r];
+            if (r && d != KEX_DEAD && ((m >> d) & 1u)) nl |= 1u << r;
+          }
+          L = nl;
+        }
+      }
+    }
+  }
+
+  // ---- exclusive scan of per-thread byte counts
+  uint32_t x = cnt;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = 0;
+    for (uint32_t w = 0; w < KEX_NT / 32; ++w) { const uint32_t v = warp_sums[w]; warp_sums[w] = t; t += v; }
+    tile_total = t;
+  }
+  __syncthreads();
+  uint32_t o = warp_sums[warp] + x - cnt;
+  const uint32_t total = tile_total;
+  const unsigned long long gbase = outoff[tile];
+  const uint32_t shift = (uint32_t)(gbase & 15ull);
+  const bool staged = (total + shift) <= KEX_STAGE;
+
+  // ---- pass C
+  for (uint32_t j = 0; j < cnt_pos; ++j) {
+    const uint32_t a = act_sm[j * KEX_NT + tid];
+    const uint32_t kind = actinfo[a] & 0xFFu;
+    if (kind == KIND_NOP) continue;
+    const uint8_t sym = in_sm[lo + j];
+    if (kind == KIND_OUTSYM) {
+      if (staged) stage[shift + o] = sym; else out[gbase + o] = sym;
+      ++o;
+      continue;
+    }
+    uint32_t m = 1u;
+    if (MB && kind == KIND_GENERAL)
+      m = (MB == 1) ? (uint32_t)mask_sm[j * KEX_NT + tid] : ((const uint32_t *)mask_sm)[j * KEX_NT + tid];
+    const ActHdr h = P.acts[a];
+    for (uint32_t k = 0; k < h.npieces; ++k) {
+      const Piece pc = P.pieces[h.piece_off + k];
+      if (!((m >> pc.target) & 1u)) continue;
+      if (pc.kind == PIECE_SYM) {
+        if (staged) stage[shift + o] = sym; else out[gbase + o] = sym;
+        ++o;
+      } else {
+        const uint8_t *c = P.consts + pc.off;
+        for (uint32_t t = 0; t < pc.len; ++t) {
+          if (staged) stage[shift + o + t] = c[t]; else out[gbase + o + t] = c[t];
+        }
+        o += pc.len;
+      }
+    }
+  }
+  if (!staged) return;
+  __syncthreads();
+  // ---- staging window -> global, 16-byte words aligned to the destination
+  uint8_t *gal = out + (gbase - shift);
+  const uint32_t end = shift + total;
+  const uint32_t w_lo = shift ? 1u : 0u;
+  const uint32_t w_hi = end >> 4;
+  for (uint32_t w = w_lo + tid; w < w_hi; w += KEX_NT)
+    *(uint4 *)(gal + 16u * w) = *(const uint4 *)(stage + 16u * w);
+  if (shift) {
+    const uint32_t he = (end < 16u) ? end : 16u;
+    for (uint32_t b = shift + tid; b < he; b += KEX_NT) gal[b] = stage[b];
+  }
+  if (w_hi >= w_lo) {
+    for (uint32_t b = (w_hi << 4) + tid; b < end; b += KEX_NT)
+      if (b >= shift) gal[b] = stage[b];
+  }
+}
+
+__global__ void k_copy_tail(const uint8_t *__restrict__ src, uint32_t len, uint8_t *__restrict__ dst) {
+  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
+}
+
+// =================================================================== host
+struct PhaseHost {
+  PhaseDev dev;
+  std::vector<int32_t> fin;          // final action per state or -1
+  std::vector<ActHdr> acts;
+  std::vector<uint8_t> fate;
+  std::vector<Piece> pieces;
+  std::vector<uint8_t> consts;
+  void *d_blob = nullptr;            // device copy of the phase blob
+  void *d_extra = nullptr;           // derived tables (nextpm, actinfo, img_*)
+  size_t smem_walk = 0, smem_maps = 0, smem_emit = 0;
+  int mask_bytes = 0;
+};
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct kex_program {
+  int device = 0;
+  std::vector<PhaseHost> phases;
+  std::string cuda_err;
+  uint32_t launches = 0;
+  bool timing = false;
+  float ms[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[8];
+  bool ev_ok = false;
+  // scratch (grow-only)
+  Buf maps[8], starts[8], fates[8], lives[8];
+  Buf samples, pend, resolved, fail, outlen, outoff, bsum, res_dev, inter[2], hostio_in, hostio_out;
+  RunResult *res_host = nullptr;
+  // shard state between the three shard calls
+  const uint8_t *sh_in = nullptr;
+  size_t sh_n = 0, sh_nchunks = 0;
+  size_t lvl_count[8];
+  int nlevels = 0;
+  uint32_t sh_phase = 0;
+};
+
+#define CK(call)                                                              \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      p->cuda_err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+      return KEX_ERR_CUDA;                                                    \
+    }                                                                         \
+  } while (0)
+
+static int ensure(kex_program *p, Buf &b, size_t bytes) {
+  if (bytes <= b.cap) return KEX_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return KEX_OK;
+}
+
+static uint32_t rd32(const uint8_t *b, size_t off) {
+  uint32_t v;
+  memcpy(&v, b + off, 4);
+  return v;
+}
+
+static int load_phase(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
+  if (len < 96 || rd32(b, 0) != 0x5058454Bu || rd32(b, 4) != 1u) return KEX_ERR_BAD_BLOB;
+  const uint32_t Q = rd32(b, 8), C = rd32(b, 12), R = rd32(b, 16), A = rd32(b, 20);
+  const uint32_t npieces = rd32(b, 24), nconst = rd32(b, 28), init = rd32(b, 32), maxout = rd32(b, 36);
+  uint32_t off[8];
+  for (int i = 0; i < 8; ++i) off[i] = rd32(b, 40 + 4 * i);
+  const uint32_t total = rd32(b, 72);
+  if (total != len || R == 0 || R > 32 || Q >= 0xFFFF || A >= 0xFFFF || C == 0 || C > 256 || init >= Q)
+    return KEX_ERR_BAD_BLOB;
+  const uint32_t Q1 = Q + 1;
+  if ((size_t)off[0] + 256 > len || (size_t)off[1] + 4ull * Q1 * C > len || (size_t)off[2] + 4ull * Q1 > len ||
+      (size_t)off[3] + sizeof(ActHdr) * (size_t)A > len || (size_t)off[4] + (size_t)A * R > len ||
+      (size_t)off[5] + 4ull * A * R > len || (size_t)off[6] + 8ull * npieces > len ||
+      (size_t)off[7] + nconst > len)
+    return KEX_ERR_BAD_BLOB;
+  if ((size_t)Q1 * C >= 65536) return KEX_ERR_UNSUPPORTED;
+  const uint32_t *trans = (const uint32_t *)(b + off[1]);
+  ph.fin.assign((const int32_t *)(b + off[2]), (const int32_t *)(b + off[2]) + Q1);
+  ph.acts.assign((const ActHdr *)(b + off[3]), (const ActHdr *)(b + off[3]) + A);
+  ph.fate.assign(b + off[4], b + off[4] + (size_t)A * R);
+  ph.pieces.assign((const Piece *)(b + off[6]), (const Piece *)(b + off[6]) + npieces);
+  ph.consts.assign(b + off[7], b + off[7] + nconst);
+  for (uint32_t i = 0; i < Q1 * C; ++i)
+    if ((trans[i] & 0xFFFFu) > Q || (trans[i] >> 16) >= A) return KEX_ERR_BAD_BLOB;
+  for (uint32_t a = 0; a < A; ++a) {
+    if ((size_t)ph.acts[a].piece_off + ph.acts[a].npieces > npieces || ph.acts[a].kind > 3) return KEX_ERR_BAD_BLOB;
+    if (ph.acts[a].outlen0 >= (1u << 24)) return KEX_ERR_UNSUPPORTED;
+  }
+  for (auto &pc : ph.pieces)
+    if (pc.target >= R || (pc.kind == PIECE_CONST && (size_t)pc.off + pc.len > nconst)) return KEX_ERR_BAD_BLOB;
+  for (int32_t f : ph.fin) if (f >= (int32_t)A) return KEX_ERR_BAD_BLOB;
+
+  // derived tables
+  std::vector<uint16_t> nextpm((size_t)Q1 * C);
+  for (uint32_t i = 0; i < Q1 * C; ++i) nextpm[i] = (uint16_t)((trans[i] & 0xFFFFu) * C);
+  std::vector<uint32_t> actinfo(A);
+  for (uint32_t a = 0; a < A; ++a) actinfo[a] = ph.acts[a].kind | (ph.acts[a].outlen0 << 8);
+  std::vector<uint32_t> img_cnt(C, 0);
+  std::vector<uint16_t> img_state((size_t)C * Q, (uint16_t)(Q * C));
+  std::vector<uint16_t> img_idx((size_t)C * Q1, 0xFFFF);
+  for (uint32_t c = 0; c < C; ++c) {
+    for (uint32_t q = 0; q < Q; ++q) {
+      const uint32_t t = trans[q * C + c] & 0xFFFFu;
+      if (t == Q) continue;
+      uint32_t k = 0;
+      for (; k < img_cnt[c]; ++k) if (img_state[(size_t)c * Q + k] == t * C) break;
+      if (k == img_cnt[c]) img_state[(size_t)c * Q + img_cnt[c]++] = (uint16_t)(t * C);
+      img_idx[(size_t)c * Q1 + q] = (uint16_t)k;
+    }
+  }
+  CK(cudaMalloc(&ph.d_blob, len));
+  CK(cudaMemcpy(ph.d_blob, b, len, cudaMemcpyHostToDevice));
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_next = 0, o_info = al(o_next + nextpm.size() * 2), o_cnt = al(o_info + actinfo.size() * 4),
+               o_ist = al(o_cnt + img_cnt.size() * 4), o_iidx = al(o_ist + img_state.size() * 2),
+               tot = al(o_iidx + img_idx.size() * 2);
+  std::vector<uint8_t> extra(tot, 0);
+  memcpy(extra.data() + o_next, nextpm.data(), nextpm.size() * 2);
+  memcpy(extra.data() + o_info, actinfo.data(), actinfo.size() * 4);
+  memcpy(extra.data() + o_cnt, img_cnt.data(), img_cnt.size() * 4);
+  memcpy(extra.data() + o_ist, img_state.data(), img_state.size() * 2);
+  memcpy(extra.data() + o_iidx, img_idx.data(), img_idx.size() * 2);
+  CK(cudaMalloc(&ph.d_extra, tot));
+  CK(cudaMemcpy(ph.d_extra, extra.data(), tot, cudaMemcpyHostToDevice));
+  const uint8_t *db = (const uint8_t *)ph.d_blob, *de = (const uint8_t *)ph.d_extra;
+  PhaseDev &d = ph.dev;
+  d.Q = Q; d.C = C; d.R = R; d.A = A; d.init = init; d.max_out = maxout;
+  d.cls = db + off[0];
+  d.trans = (const uint32_t *)(db + off[1]);
+  d.acts = (const ActHdr *)(db + off[3]);
+  d.fate = db + off[4];
+  d.addlen = (const uint32_t *)(db + off[5]);
+  d.pieces = (const Piece *)(db + off[6]);
+  d.consts = db + off[7];
+  d.nextpm = (const uint16_t *)(de + o_next);
+  d.actinfo = (const uint32_t *)(de + o_info);
+  d.img_cnt = (const uint32_t *)(de + o_cnt);
+  d.img_state = (const uint16_t *)(de + o_ist);
+  d.img_idx = (const uint16_t *)(de + o_iidx);
+  ph.mask_bytes = (R == 1) ? 0 : (R <= 8 ? 1 : 4);
+  ph.smem_maps = 256 + al((size_t)Q1 * C * 2);
+  ph.smem_walk = 256 + (size_t)Q1 * C * 4 + (size_t)A * 4;
+  ph.smem_emit = KEX_CHUNK + KEX_STAGE + 32 + (size_t)KEX_CHUNK * 2 + (size_t)KEX_CHUNK * ph.mask_bytes +
+                 (ph.mask_bytes ? 2u * KEX_NT * 32u : 0u) + (size_t)Q1 * C * 4 + (size_t)A * 4 + 256;
+  if (ph.smem_emit > 200 * 1024 || ph.smem_walk > 200 * 1024) return KEX_ERR_UNSUPPORTED;
+  return KEX_OK;
+}
+
+extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_program **out) {
+  if (!blob || !out || blob_len < 16) return KEX_ERR_ARG;
+  const uint8_t *b = (const uint8_t *)blob;
+  if (rd32(b, 0) != 0x4C58454Bu || rd32(b, 4) != 1u) return KEX_ERR_BAD_BLOB;
+  const uint32_t nph = rd32(b, 8);
+  if (nph == 0 || nph > 64 || rd32(b, 12) != blob_len || 16 + 8ull * nph > blob_len) return KEX_ERR_BAD_BLOB;
+  kex_program *p = new kex_program();
+  p->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete p; return KEX_ERR_CUDA; }
+  p->phases.resize(nph);
+  for (uint32_t i = 0; i < nph; ++i) {
+    const uint32_t off = rd32(b, 16 + 8 * i), len = rd32(b, 20 + 8 * i);
+    int rc = ((size_t)off + len > blob_len) ? KEX_ERR_BAD_BLOB : load_phase(p, b + off, len, p->phases[i]);
+    if (rc != KEX_OK) { kex_free(p); return rc; }
+  }
+  size_t mx_walk = 0, mx_maps = 0, mx_e0 = 0, mx_e1 = 0, mx_e4 = 0;
+  for (auto &ph : p->phases) {
+    if (ph.smem_walk > mx_walk) mx_walk = ph.smem_walk;
+    if (ph.smem_maps > mx_maps) mx_maps = ph.smem_maps;
+    size_t &m = (ph.mask_bytes == 0) ? mx_e0 : (ph.mask_bytes == 1 ? mx_e1 : mx_e4);
+    if (ph.smem_emit > m) m = ph.smem_emit;
+  }
+  cudaFuncSetAttribute(k_chunk_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_maps);
+  cudaFuncSetAttribute(k_true_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_walk);
+  if (mx_e0) cudaFuncSetAttribute(k_emit<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_e0);
+  if (mx_e1) cudaFuncSetAttribute(k_emit<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_e1);
+  if (mx_e4) cudaFuncSetAttribute(k_emit<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_e4);
+  if (cudaMallocHost((void **)&p->res_host, sizeof(RunResult)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&p->ev[i]);
+  p->ev_ok = true;
+  *out = p;
+  return KEX_OK;
+}
+
+extern "C" void kex_free(kex_program *p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (auto &ph : p->phases) { cudaFree(ph.d_blob); cudaFree(ph.d_extra); }
+  for (int i = 0; i < 8; ++i) { cudaFree(p->maps[i].p); cudaFree(p->starts[i].p); cudaFree(p->fates[i].p); cudaFree(p->lives[i].p); }
+  Buf *bs[] = {&p->samples, &p->pend, &p->resolved, &p->fail, &p->outlen, &p->outoff, &p->bsum, &p->res_dev,
+               &p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out};
+  for (Buf *b : bs) cudaFree(b->p);
+  if (p->res_host) cudaFreeHost(p->res_host);
+  if (p->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(p->ev[i]);
+  delete p;
+}
+
+extern "C" int kex_info(const kex_program *p, uint32_t phase, kex_info_t *info) {
+  if (!p || !info || phase >= p->phases.size()) return KEX_ERR_ARG;
+  const PhaseDev &d = p->phases[phase].dev;
+  info->nphases = (uint32_t)p->phases.size();
+  info->nstates = d.Q; info->nclasses = d.C; info->nregs = d.R; info->nactions = d.A;
+  info->max_out_per_byte = d.max_out; info->chunk_bytes = KEX_CHUNK; info->reserved = 0;
+  return KEX_OK;
+}
+
+extern "C" int kex_final_action(const kex_program *p, uint32_t state, int *accepting, uint32_t *flush_mask,
+                                const uint8_t **tail, size_t *tail_len) {
+  if (!p) return KEX_ERR_ARG;
+  const PhaseHost &ph = p->phases[p->sh_phase];
+  if (state > ph.dev.Q) return KEX_ERR_ARG;
+  const int32_t a = ph.fin[state];
+  if (accepting) *accepting = a >= 0;
+  if (flush_mask) *flush_mask = a >= 0 ? ph.acts[a].flush_mask : 0u;
+  // the tail is the concatenation of the action's constant pieces (all target the stream)
+  static thread_local std::vector<uint8_t> buf;
+  buf.clear();
+  if (a >= 0)
+    for (uint32_t k = 0; k < ph.acts[a].npieces; ++k) {
+      const Piece &pc = ph.pieces[ph.acts[a].piece_off + k];
+      buf.insert(buf.end(), ph.consts.begin() + pc.off, ph.consts.begin() + pc.off + pc.len);
+    }
+  if (tail) *tail = buf.data();
+  if (tail_len) *tail_len = buf.size();
+  return KEX_OK;
+}
+
+extern "C" size_t kex_out_bound(const kex_program *p, size_t n) {
+  if (!p) return 0;
+  size_t cur = n;
+  for (auto &ph : p->phases) {
+    size_t tail = 0;
+    for (auto &a : ph.acts) if (a.total_len > tail) tail = a.total_len;
+    cur = cur * ph.dev.max_out + tail;
+  }
+  return cur;
+}
+
+extern "C" uint32_t kex_last_launch_count(const kex_program *p) { return p ? p->launches : 0; }
+extern "C" int kex_set_timing(kex_program *p, int enabled) { if (!p) return KEX_ERR_ARG; p->timing = enabled != 0; return KEX_OK; }
+extern "C" float kex_last_kernel_ms(const kex_program *p, uint32_t which) { return (p && which < 4) ? p->ms[which] : 0.f; }
+extern "C" const char *kex_last_cuda_error(const kex_program *p) { return p ? p->cuda_err.c_str() : ""; }
+extern "C" const char *kex_strerror(int code) {
+  switch (code) {
+    case KEX_OK: return "ok";
+    case KEX_ERR_BAD_BLOB: return "malformed kexprog blob";
+    case KEX_ERR_CUDA: return "CUDA runtime error";
+    case KEX_ERR_OUT_CAP: return "output buffer too small";
+    case KEX_ERR_UNSUPPORTED: return "program exceeds a device-table limit";
+    case KEX_ERR_ARG: return "bad argument";
+  }
+  return "unknown error";
+}
+
+// ---------------------------------------------------------------- shard steps
+static int do_summarize(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, cudaStream_t st) {
+  PhaseHost &ph = p->phases[phase];
+  const PhaseDev &P = ph.dev;
+  const uint32_t Q1 = P.Q + 1;
+  if (((uintptr_t)d_in & 15u) != 0) return KEX_ERR_ARG;
+  p->sh_in = d_in; p->sh_n = n; p->sh_phase = phase;
+  const size_t nchunks = (n + KEX_CHUNK - 1) / KEX_CHUNK;
+  p->sh_nchunks = nchunks;
+  // level sizes
+  p->nlevels = 0;
+  size_t c = nchunks;
+  while (true) {
+    p->lvl_count[p->nlevels++] = c;
+    if (c <= 1) break;
+    c = (c + KEX_FANIN - 1) / KEX_FANIN;
+  }
+  for (int l = 0; l < p->nlevels; ++l) {
+    int rc = ensure(p, p->maps[l], p->lvl_count[l] * Q1 * sizeof(uint16_t));
+    if (rc) return rc;
+    rc = ensure(p, p->starts[l], p->lvl_count[l] * sizeof(uint16_t));
+    if (rc) return rc;
+  }
+  int rc = ensure(p, p->res_dev, sizeof(RunResult));
+  if (rc) return rc;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], st));
+  k_chunk_maps<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_maps, st>>>(P, d_in, n, nchunks, (uint16_t *)p->maps[0].p);
+  p->launches++;
+  if (p->timing) CK(cudaEventRecord(p->ev[1], st));
+  const unsigned bt = Q1 < 32 ? 32 : (Q1 > 256 ? 256 : ((Q1 + 31) / 32 * 32));
+  for (int l = 1; l < p->nlevels; ++l) {
+    k_compose<uint16_t, false><<<(unsigned)p->lvl_count[l], bt, 0, st>>>((const uint16_t *)p->maps[l - 1].p, p->lvl_count[l - 1],
+                                                                       (uint16_t *)p->maps[l].p, Q1);
+    p->launches++;
+  }
+  CK(cudaGetLastError());
+  return KEX_OK;
+}
+
+static int do_walk(kex_program *p, uint32_t start_state, cudaStream_t st) {
+  PhaseHost &ph = p->phases[p->sh_phase];
+  const PhaseDev &P = ph.dev;
+  const uint32_t Q1 = P.Q + 1, R = P.R;
+  const size_t nchunks = p->sh_nchunks, n = p->sh_n;
+  const int top = p->nlevels - 1;
+  k_set_u16<<<1, 1, 0, st>>>((uint16_t *)p->starts[top].p, start_state);
+  p->launches++;
+  for (int l = top; l >= 1; --l) {
+    const size_t np = p->lvl_count[l];
+    k_push_states<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const uint16_t *)p->maps[l - 1].p, p->lvl_count[l - 1],
+                                                                (const uint16_t *)p->starts[l].p, np,
+                                                                (uint16_t *)p->starts[l - 1].p, Q1);
+    p->launches++;
+  }
+  int rc;
+  const size_t nsamp = nchunks * KEX_NT;
+  if ((rc = ensure(p, p->samples, nsamp * sizeof(uint16_t)))) return rc;
+  if ((rc = ensure(p, p->resolved, nchunks * sizeof(unsigned long long)))) return rc;
+  if ((rc = ensure(p, p->fail, nchunks * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(p, p->pend, nchunks * R * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(p, p->fates[0], nchunks * R))) return rc;
+  if (p->timing) CK(cudaEventRecord(p->ev[2], st));
+  k_true_walk<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_walk, st>>>(
+      P, p->sh_in, n, nchunks, (const uint16_t *)p->starts[0].p, (uint16_t *)p->samples.p, (uint8_t *)p->fates[0].p,
+      (uint32_t *)p->pend.p, (unsigned long long *)p->resolved.p, (uint32_t *)p->fail.p, (RunResult *)p->res_dev.p);
+  p->launches++;
+  if (p->timing) CK(cudaEventRecord(p->ev[3], st));
+  k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->fail.p, nchunks, (RunResult *)p->res_dev.p);
+  p->launches++;
+  CK(cudaMemcpyAsync(p->res_host, p->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return KEX_OK;
+}
+
+// fate maps of the first `nchunks_eff` chunks -> composed fate map (host, R bytes)
+static int do_fate_up(kex_program *p, size_t nchunks_eff, uint8_t *h_fate, cudaStream_t st) {
+  PhaseHost &ph = p->phases[p->sh_phase];
+  const uint32_t R = ph.dev.R;
+  if (R == 1 || nchunks_eff == 0) {
+    for (uint32_t r = 0; r < R; ++r) h_fate[r] = (uint8_t)r;
+    return KEX_OK;
+  }
+  size_t cnt[8];
+  int nl = 0;
+  size_t c = nchunks_eff;
+  while (true) { cnt[nl++] = c; if (c <= 1) break; c = (c + KEX_FANIN - 1) / KEX_FANIN; }
+  for (int l = 1; l < nl; ++l) {
+    int rc = ensure(p, p->fates[l], cnt[l] * R);
+    if (rc) return rc;
+    k_compose<uint8_t, true><<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->fates[l - 1].p, cnt[l - 1],
+                                                            (uint8_t *)p->fates[l].p, R);
+    p->launches++;
+  }
+  CK(cudaMemcpyAsync(h_fate, p->fates[nl - 1].p, R, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return KEX_OK;
+}
+
+static int do_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff, uint8_t *d_out, size_t out_cap,
+                   size_t *out_len, cudaStream_t st) {
+  PhaseHost &ph = p->phases[p->sh_phase];
+  const PhaseDev &P = ph.dev;
+  const uint32_t R = P.R;
+  *out_len = 0;
+  if (n_eff == 0) return KEX_OK;
+  const size_t nchunks = (n_eff + KEX_CHUNK - 1) / KEX_CHUNK;
+  int rc;
+  size_t cnt[8];
+  int nl = 0;
+  size_t c = nchunks;
+  while (true) { cnt[nl++] = c; if (c <= 1) break; c = (c + KEX_FANIN - 1) / KEX_FANIN; }
+  if (R > 1) {
+    for (int l = 0; l < nl; ++l) if ((rc = ensure(p, p->lives[l], cnt[l] * sizeof(uint32_t)))) return rc;
+    for (int l = 1; l < nl; ++l) if ((rc = ensure(p, p->fates[l], cnt[l] * R))) return rc;
+    // the up-sweep over exactly these chunks (a failing shard has fewer chunks than it walked)
+    for (int l = 1; l < nl; ++l) {
+      k_compose<uint8_t, true><<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->fates[l - 1].p, cnt[l - 1],
+                                                              (uint8_t *)p->fates[l].p, R);
+      p->launches++;
+    }
+    k_set_u32<<<1, 1, 0, st>>>((uint32_t *)p->lives[nl - 1].p, live_end_mask);
+    p->launches++;
+    for (int l = nl - 1; l >= 1; --l) {
+      k_push_live<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, st>>>((const uint8_t *)p->fates[l - 1].p, cnt[l - 1],
+                                                                   (const uint32_t *)p->lives[l].p, cnt[l],
+                                                                   (uint32_t *)p->lives[l - 1].p, R);
+      p->launches++;
+    }
+  } else {
+    if ((rc = ensure(p, p->lives[0], sizeof(uint32_t)))) return rc;
+  }
+  if ((rc = ensure(p, p->outlen, nchunks * 8))) return rc;
+  if ((rc = ensure(p, p->outoff, (nchunks + 1) * 8))) return rc;
+  const size_t nb = (nchunks + SCAN_TILE - 1) / SCAN_TILE;
+  if ((rc = ensure(p, p->bsum, nb * 8))) return rc;
+  k_outlen<<<(unsigned)((nchunks + 255) / 256), 256, 0, st>>>((const uint32_t *)p->pend.p, (const unsigned long long *)p->resolved.p,
+                                                             (const uint32_t *)p->lives[0].p, nchunks, R,
+                                                             (unsigned long long *)p->outlen.p);
+  k_scan_sums<<<(unsigned)nb, SCAN_THREADS, 0, st>>>((const unsigned long long *)p->outlen.p, nchunks, (unsigned long long *)p->bsum.p);
+  k_scan_top<<<1, SCAN_THREADS, 0, st>>>((unsigned long long *)p->bsum.p, nb, (RunResult *)p->res_dev.p);
+  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, st>>>((const unsigned long long *)p->outlen.p, nchunks,
+                                                     (const unsigned long long *)p->bsum.p, (unsigned long long *)p->outoff.p);
+  p->launches += 4;
+  CK(cudaMemcpyAsync(p->res_host, p->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const size_t total = (size_t)p->res_host->total_out;
+  *out_len = total;
+  if (total > out_cap) return KEX_ERR_OUT_CAP;
+  if (p->timing) CK(cudaEventRecord(p->ev[4], st));
+  const unsigned grid = (unsigned)nchunks;
+  if (ph.mask_bytes == 0)
+    k_emit<0><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->sh_in, n_eff, (const uint16_t *)p->samples.p,
+                                                  (const unsigned long long *)p->outoff.p, (const uint32_t *)p->lives[0].p, d_out);
+  else if (ph.mask_bytes == 1)
+    k_emit<1><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->sh_in, n_eff, (const uint16_t *)p->samples.p,
+                                                  (const unsigned long long *)p->outoff.p, (const uint32_t *)p->lives[0].p, d_out);
+  else
+    k_emit<4><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->sh_in, n_eff, (const uint16_t *)p->samples.p,
+                                                  (const unsigned long long *)p->outoff.p, (const uint32_t *)p->lives[0].p, d_out);
+  p->launches++;
+  if (p->timing) CK(cudaEventRecord(p->ev[5], st));
+  CK(cudaGetLastError());
+  return KEX_OK;
+}
+
+extern "C" int kex_shard_summarize(kex_program *p, const uint8_t *d_in, size_t n, uint16_t *h_state_map, void *stream) {
+  if (!p || !h_state_map || (n && !d_in)) return KEX_ERR_ARG;
+  if (p->phases.size() != 1) return KEX_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  p->launches = 0;
+  const uint32_t Q1 = p->phases[0].dev.Q + 1;
+  if (n == 0) {
+    p->sh_in = d_in; p->sh_n = 0; p->sh_nchunks = 0; p->sh_phase = 0;
+    for (uint32_t q = 0; q < Q1; ++q) h_state_map[q] = (uint16_t)q;
+    return KEX_OK;
+  }
+  int rc = do_summarize(p, 0, d_in, n, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_state_map, p->maps[p->nlevels - 1].p, Q1 * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return KEX_OK;
+}
+
+extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *end_state, size_t *fail_pos,
+                              uint8_t *h_fate_map, void *stream) {
+  if (!p || !end_state || !fail_pos || !h_fate_map) return KEX_ERR_ARG;
+  CK(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const PhaseDev &P = p->phases[p->sh_phase].dev;
+  if (start_state > P.Q) return KEX_ERR_ARG;
+  if (p->sh_n == 0) {
+    *end_state = start_state; *fail_pos = (size_t)-1;
+    for (uint32_t r = 0; r < P.R; ++r) h_fate_map[r] = (uint8_t)r;
+    return KEX_OK;
+  }
+  int rc = do_walk(p, start_state, st);
+  if (rc) return rc;
+  const unsigned long long f = p->res_host->fail_pos;
+  *fail_pos = (f == KEX_NONE64) ? (size_t)-1 : (size_t)f;
+  *end_state = p->res_host->end_state;
+  const size_t n_eff = (f == KEX_NONE64) ? p->sh_n : (size_t)f;
+  return do_fate_up(p, (n_eff + KEX_CHUNK - 1) / KEX_CHUNK, h_fate_map, st);
+}
+
+extern "C" int kex_shard_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff, uint8_t *d_out, size_t out_cap,
+                              size_t *out_len, void *stream) {
+  if (!p || !out_len || n_eff > p->sh_n) return KEX_ERR_ARG;
+  CK(cudaSetDevice(p->device));
+  return do_emit(p, live_end_mask, n_eff, d_out, out_cap, out_len, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------ whole pipeline
+static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
+                     size_t *out_len, int *status, size_t *fail_count, cudaStream_t st) {
+  PhaseHost &ph = p->phases[phase];
+  const PhaseDev &P = ph.dev;
+  p->sh_phase = phase;
+  uint32_t end_state = P.init;
+  size_t n_eff = n;
+  bool failed = false;
+  if (n > 0) {
+    int rc = do_summarize(p, phase, d_in, n, st);
+    if (rc) return rc;
+    if ((rc = do_walk(p, P.init, st))) return rc;
+    const unsigned long long f = p->res_host->fail_pos;
+    if (f != KEX_NONE64) { failed = true; n_eff = (size_t)f; }
+    end_state = p->res_host->end_state;
+  } else {
+    p->sh_in = d_in; p->sh_n = 0; p->sh_nchunks = 0;
+  }
+  const int32_t fa = failed ? -1 : ph.fin[end_state];
+  const bool accept = fa >= 0;
+  const uint32_t live = accept ? ph.acts[fa].flush_mask : 0u;
+  size_t body = 0;
+  int rc = do_emit(p, live, n_eff, d_out, out_cap, &body, st);
+  if (rc == KEX_ERR_OUT_CAP) { *out_len = body + (accept ? ph.acts[fa].total_len : 0); return rc; }
+  if (rc) return rc;
+  if (accept) {
+    const ActHdr &h = ph.acts[fa];
+    size_t o = body;
+    size_t tail = 0;
+    for (uint32_t k = 0; k < h.npieces; ++k) tail += ph.pieces[h.piece_off + k].len;
+    if (body + tail > out_cap) { *out_len = body + tail; return KEX_ERR_OUT_CAP; }
+    for (uint32_t k = 0; k < h.npieces; ++k) {
+      const Piece &pc = ph.pieces[h.piece_off + k];
+      k_copy_tail<<<1, 64, 0, st>>>(P.consts + pc.off, pc.len, d_out + o);
+      p->launches++;
+      o += pc.len;
+    }
+    *out_len = o;
+    *status = KEX_ACCEPT;
+    *fail_count = 0;
+  } else {
+    *out_len = body / 16384 * 16384;   // whole 16 KiB flushes only (crt.c:140-159, 217-227)
+    *status = KEX_REJECT;
+    *fail_count = n_eff;
+  }
+  return KEX_OK;
+}
+
+extern "C" int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
+                              size_t *out_len, int *status, size_t *fail_count, void *stream) {
+  if (!p || !out_len || !status || !fail_count || (n && !d_in)) return KEX_ERR_ARG;
+  CK(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  p->launches = 0;
+  for (int i = 0; i < 4; ++i) p->ms[i] = 0.f;
+  if (p->timing) CK(cudaEventRecord(p->ev[6], st));
+  const uint8_t *cur = d_in;
+  size_t cur_n = n;
+  const size_t nph = p->phases.size();
+  for (size_t i = 0; i < nph; ++i) {
+    uint8_t *dst = d_out;
+    size_t cap = out_cap;
+    if (i + 1 < nph) {
+      // intermediate stream: grow until it fits (the exact size is known before emit)
+      Buf &b = p->inter[i & 1];
+      size_t guess = cur_n * 2 + 65536;
+      if (b.cap < guess) { int rc = ensure(p, b, guess); if (rc) return rc; }
+      dst = (uint8_t *)b.p;
+      cap = b.cap;
+    }
+    size_t ol = 0, fc = 0;
+    int stt = 0;
+    int rc = run_phase(p, (uint32_t)i, cur, cur_n, dst, cap, &ol, &stt, &fc, st);
+    if (rc == KEX_ERR_OUT_CAP && i + 1 < nph) {
+      Buf &b = p->inter[i & 1];
+      CK(cudaStreamSynchronize(st));
+      if ((rc = ensure(p, b, ol + 65536))) return rc;
+      dst = (uint8_t *)b.p;
+      cap = b.cap;
+      rc = run_phase(p, (uint32_t)i, cur, cur_n, dst, cap, &ol, &stt, &fc, st);
+    }
+    if (rc) { *out_len = ol; return rc; }
+    // a rejecting phase hands its truncated stream to the next phase, and the
+    // pipeline's exit status is the last phase's (crt.c:414-455)
+    *status = stt;
+    *fail_count = fc;
+    *out_len = ol;
+    cur = dst;
+    cur_n = ol;
+  }
+  if (p->timing) {
+    CK(cudaEventRecord(p->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    if (p->sh_n) {
+      cudaEventElapsedTime(&p->ms[0], p->ev[0], p->ev[1]);
+      cudaEventElapsedTime(&p->ms[1], p->ev[2], p->ev[3]);
+      if (*out_len) cudaEventElapsedTime(&p->ms[2], p->ev[4], p->ev[5]);
+    }
+    cudaEventElapsedTime(&p->ms[3], p->ev[6], p->ev[7]);
+  }
+  CK(cudaStreamSynchronize(st));
+  return KEX_OK;
+}
+
+extern "C" int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n, uint8_t *h_out, size_t out_cap,
+                            size_t *out_len, int *status, size_t *fail_count) {
+  if (!p || !out_len || !status || !fail_count || (n && !h_in)) return KEX_ERR_ARG;
+  CK(cudaSetDevice(p->device));
+  int rc;
+  if ((rc = ensure(p, p->hostio_in, n + 16))) return rc;
+  if ((rc = ensure(p, p->hostio_out, out_cap + 16))) return rc;
+  if (n) CK(cudaMemcpy(p->hostio_in.p, h_in, n, cudaMemcpyHostToDevice));
+  rc = kex_run_device(p, (const uint8_t *)p->hostio_in.p, n, (uint8_t *)p->hostio_out.p, out_cap, out_len, status,
+                      fail_count, nullptr);
+  if (rc) return rc;
+  if (*out_len) CK(cudaMemcpy(h_out, p->hostio_out.p, *out_len, cudaMemcpyDeviceToHost));
+  return KEX_OK;
+}

@@ -1,0 +1,329 @@
+"""SST pipeline -> `kexprog` blob: the serialised transition and
+register-action tables the CUDA back end loads (`kex_load`, include/kexcuda.h).
+
+This takes the role `compileProgram` has in the reference
+(src/KMC/Program/Backends/C.hs:529-540): it consumes the determinized,
+optimised SSTs of a pipeline and produces the executable
+artefact.  Where the C back end prints one goto-labelled block per state, the
+blob holds dense tables:
+
+  cls[256]            byte -> byte class (coarsest partition of all predicates,
+                      src/KMC/Theories.hs:58-80)
+  trans[(Q+1)*C]      (next state | action id << 16); state Q is the FAIL sink
+  final[Q+1]          action applied at end of input, or -1 = reject
+  acts[A]             per action: kind, piece range, bytes appended to out
+  fate[A*R]           where the *old* content of register r goes: a register
+                      index, 0 = flushed to the output stream, 0xFF = dropped
+  addlen[A*R]         bytes newly appended to each register
+  pieces[]            (target register, const|sym, length, const offset) in
+                      output order
+  consts[]            literal bytes
+
+Register updates of path-tree SSTs have the shape  x := y1 .. yk new1 .. newm
+(old registers first, in ancestor order, then new material;
+src/KMC/Determinization.hs:165-183), so every byte that reaches the output
+does so in the order it was created.  `check_chronological` verifies the
+shape; the CUDA back end relies on it to let the chunk that *creates* a byte
+write it.
+"""
+import struct
+
+from .frontend import byteset as BS
+
+MAGIC_PHASE = 0x5058454B      # "KEXP"
+MAGIC_PIPE = 0x4C58454B       # "KEXL"
+VERSION = 1
+DEAD = 0xFF
+MAX_REGS = 32
+
+KIND_NOP, KIND_OUTSYM, KIND_OUTONLY, KIND_GENERAL = 0, 1, 2, 3
+PIECE_CONST, PIECE_SYM = 0, 1
+
+
+class UnsupportedProgram(Exception):
+    pass
+
+
+def check_chronological(sst):
+    def ok(atoms):
+        new = False
+        for a in atoms:
+            if a[0] == "v":
+                if new:
+                    return False
+            else:
+                new = True
+        return True
+    for es in sst.edges.values():
+        for _, upd, _ in es:
+            if not all(ok(w) for w in upd.values()):
+                return False
+    return all(ok(w) for w in sst.final.values())
+
+
+def liveness(sst):
+    """Backward dataflow: live[q] = registers whose content at state q can
+    still reach the output."""
+    live = {q: set() for q in range(sst.nstates)}
+    for q, w in sst.final.items():
+        live[q].update(a[1] for a in w if a[0] == "v")
+    changed = True
+    while changed:
+        changed = False
+        for q, es in sst.edges.items():
+            cur = live[q]
+            n0 = len(cur)
+            for _, upd, q2 in es:
+                l2 = live[q2]
+                for r2, w in upd.items():
+                    if r2 == 0 or r2 in l2:
+                        cur.update(a[1] for a in w if a[0] == "v")
+                for r in l2:
+                    if r not in upd:
+                        cur.add(r)
+            if len(cur) != n0:
+                changed = True
+    for s in live.values():
+        s.discard(0)
+    return live
+
+
+class PhaseTables:
+    """Plain-Python view of one phase's tables (also used by the tests'
+    algorithm model)."""
+    pass
+
+
+def build_phase(sst) -> PhaseTables:
+    if not check_chronological(sst):
+        raise UnsupportedProgram("register update not in (old registers)(new material) form")
+    live = liveness(sst)
+    Q = sst.nstates
+    if Q >= 0xFFFF:
+        raise UnsupportedProgram("too many states for 16-bit state ids")
+    R = 1 + max([len(s) for s in live.values()] + [0])
+    if R > MAX_REGS:
+        raise UnsupportedProgram("%d simultaneously live registers exceed the device limit of %d" % (R, MAX_REGS))
+    # Per-state register allocation: a register keeps the slot of the register
+    # whose content it inherits whenever that slot is free, so that most
+    # transitions stay identity moves.  Slot 0 is always the output stream.
+    alloc = {sst.initial: {}}
+    order = [sst.initial]
+    i = 0
+    while i < len(order):
+        q = order[i]
+        i += 1
+        for _, upd, q2 in sst.edges.get(q, ()):
+            if q2 in alloc:
+                continue
+            src = alloc[q]
+            want = {}
+            for v in sorted(live[q2]):
+                if v not in upd:
+                    want[v] = src.get(v)
+                else:
+                    w = upd[v]
+                    want[v] = src.get(w[0][1]) if w and w[0][0] == "v" else None
+            slots = {}
+            taken = set()
+            for v in sorted(live[q2]):
+                if want[v] is not None and want[v] not in taken:
+                    slots[v] = want[v]
+                    taken.add(want[v])
+            free = [k for k in range(1, R) if k not in taken]
+            for v in sorted(live[q2]):
+                if v not in slots:
+                    slots[v] = free.pop(0)
+            alloc[q2] = slots
+            order.append(q2)
+    for q in range(Q):
+        alloc.setdefault(q, {v: k + 1 for k, v in enumerate(sorted(live[q]))})
+
+    preds = sorted({p for es in sst.edges.values() for p, _, _ in es})
+    parts = BS.coarsest_partition(preds)
+    covered = 0
+    for p in parts:
+        covered |= p
+    if BS.complement(covered):
+        parts.append(BS.complement(covered))
+    C = len(parts)
+    cls = [0] * 256
+    for ci, p in enumerate(parts):
+        for b in BS.to_list(p):
+            cls[b] = ci
+
+    consts = bytearray()
+    const_off = {}
+
+    def intern_const(bs):
+        bs = bytes(bs)
+        if bs not in const_off:
+            const_off[bs] = len(consts)
+            consts.extend(bs)
+        return const_off[bs]
+
+    actions = []      # (kind, fate tuple, addlen tuple, pieces tuple)
+    action_id = {}
+
+    def make_action(upd, live_src, live_dst, asrc, adst):
+        fate = [DEAD] * R
+        fate[0] = 0
+        pieces = []
+        addlen = [0] * R
+        seen = set()
+        assigned = set()
+        for v in sorted(upd):
+            if v != 0 and v not in live_dst:
+                continue
+            assigned.add(v)
+            tgt = 0 if v == 0 else adst[v]
+            for a in upd[v]:
+                if a[0] == "v":
+                    if a[1] == 0:
+                        if v != 0:
+                            raise UnsupportedProgram("output register read into a register")
+                        continue
+                    if a[1] in seen:
+                        raise UnsupportedProgram("register update is not copyless")
+                    seen.add(a[1])
+                    if a[1] in asrc:
+                        fate[asrc[a[1]]] = tgt
+                elif a[0] == "c":
+                    pieces.append((tgt, PIECE_CONST, len(a[1]), intern_const(a[1])))
+                    addlen[tgt] += len(a[1])
+                else:
+                    pieces.append((tgt, PIECE_SYM, 1, 0))
+                    addlen[tgt] += 1
+        if 0 in upd and (not upd[0] or upd[0][0] != ("v", 0)):
+            raise UnsupportedProgram("output register is reset by an update")
+        for v in live_dst:
+            if v not in assigned:
+                if v in seen:
+                    raise UnsupportedProgram("register update is not copyless")
+                fate[asrc[v]] = adst[v]
+        ident = all(fate[asrc[v]] == asrc[v] for v in live_src)
+        if not pieces and ident:
+            kind = KIND_NOP
+        elif ident and len(pieces) == 1 and pieces[0][:2] == (0, PIECE_SYM):
+            kind = KIND_OUTSYM
+        elif ident and all(p[0] == 0 for p in pieces):
+            kind = KIND_OUTONLY
+        else:
+            kind = KIND_GENERAL
+        if kind != KIND_GENERAL:
+            # content of registers that are not live is irrelevant; make the
+            # fate row a clean identity so consumers can skip it
+            fate = list(range(R))
+        key = (kind, tuple(fate), tuple(addlen), tuple(pieces))
+        if key not in action_id:
+            action_id[key] = len(actions)
+            actions.append(key)
+        return action_id[key]
+
+    nop = make_action({}, set(), set(), {}, {})
+    assert nop == 0
+    FAIL = Q
+    trans = [(FAIL | (nop << 16))] * ((Q + 1) * C)
+    for q, es in sst.edges.items():
+        for p, upd, q2 in es:
+            a = make_action(upd, live[q], live[q2], alloc[q], alloc[q2])
+            for ci, part in enumerate(parts):
+                if part & p:
+                    assert BS.is_subset(part, p)
+                    assert trans[q * C + ci] == (FAIL | (nop << 16)), "non-deterministic SST"
+                    trans[q * C + ci] = q2 | (a << 16)
+    final = [-1] * (Q + 1)
+    for q, w in sst.final.items():
+        final[q] = make_action({0: (("v", 0),) + tuple(w)}, live[q], set(), alloc[q], {})
+    if len(actions) >= 0xFFFF:
+        raise UnsupportedProgram("too many distinct actions")
+
+    t = PhaseTables()
+    t.Q, t.C, t.R, t.A = Q, C, R, len(actions)
+    t.init = sst.initial
+    t.cls = cls
+    t.trans = trans
+    t.final = final
+    t.kind = [a[0] for a in actions]
+    t.fate = [list(a[1]) for a in actions]
+    t.addlen = [list(a[2]) for a in actions]
+    t.pieces = [list(a[3]) for a in actions]
+    t.consts = bytes(consts)
+    t.max_out_per_byte = max([sum(a[2]) for a in actions] + [1])
+    return t
+
+
+def serialize_phase(t: PhaseTables) -> bytes:
+    piece_off = []
+    flat = []
+    for ps in t.pieces:
+        piece_off.append(len(flat))
+        flat.extend(ps)
+    sections = []
+    sections.append(bytes(t.cls))
+    sections.append(struct.pack("<%dI" % len(t.trans), *t.trans))
+    sections.append(struct.pack("<%di" % len(t.final), *t.final))
+    acts = bytearray()
+    for a in range(t.A):
+        flush = 0
+        for r in range(1, t.R):
+            if t.fate[a][r] == 0:
+                flush |= 1 << r
+        acts += struct.pack("<IIIIII", t.kind[a], len(t.pieces[a]), piece_off[a],
+                            t.addlen[a][0], flush, sum(t.addlen[a]))
+    sections.append(bytes(acts))
+    sections.append(bytes(b for row in t.fate for b in row))
+    sections.append(struct.pack("<%dI" % (t.A * t.R), *[x for row in t.addlen for x in row]))
+    sections.append(b"".join(struct.pack("<BBHI", p[0], p[1], p[2], p[3]) for p in flat))
+    sections.append(t.consts)
+    nhdr = 24
+    off = nhdr * 4
+    offs = []
+    body = bytearray()
+    for s in sections:
+        pad = (-off) % 16
+        body += b"\0" * pad
+        off += pad
+        offs.append(off)
+        body += s
+        off += len(s)
+    pad = (-off) % 16
+    body += b"\0" * pad
+    off += pad
+    hdr = [MAGIC_PHASE, VERSION, t.Q, t.C, t.R, t.A, len(flat), len(t.consts), t.init,
+           t.max_out_per_byte] + offs + [off]
+    hdr += [0] * (nhdr - len(hdr))
+    return struct.pack("<%dI" % nhdr, *hdr) + bytes(body)
+
+
+def serialize_pipeline(phases) -> bytes:
+    blobs = [serialize_phase(t) for t in phases]
+    n = len(blobs)
+    hdr_words = 4 + 2 * n
+    hdr_size = (hdr_words * 4 + 15) // 16 * 16
+    off = hdr_size
+    table = []
+    for b in blobs:
+        table += [off, len(b)]
+        off += len(b)
+    hdr = struct.pack("<%dI" % hdr_words, MAGIC_PIPE, VERSION, n, off, *table)
+    hdr += b"\0" * (hdr_size - len(hdr))
+    return hdr + b"".join(blobs)
+
+
+def compile_kex(src: str, opt: int = 3) -> bytes:
+    """`.kex` source -> kexprog blob (the CUDA counterpart of
+    `kexc compile --act=false --la=false`)."""
+    from .frontend.driver import build_ssts
+    phases = []
+    for s in build_ssts(src, opt):
+        try:
+            phases.append(build_phase(s))
+        except UnsupportedProgram:
+            if opt == 0:
+                raise
+            # constant propagation may move a literal in front of an older
+            # register; the unoptimised SST always has the required shape
+            s0 = build_ssts(src, 0)[len(phases)]
+            phases.append(build_phase(s0))
+    return serialize_pipeline(phases)

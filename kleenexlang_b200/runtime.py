@@ -1,0 +1,192 @@
+"""ctypes binding of libkexcuda.so (include/kexcuda.h) and the host-side
+mirror of the compiled-binary contract of the reference
+(crt/crt.c:372-467; src/KMC/Program/Backends/C.hs:72-83): a `CompiledProgram`
+is what `kexc compile` would have produced, `run()` is `./bin < in > out`.
+
+There is no CPU fallback: if the CUDA library is missing or fails to load the
+import of this module's entry points raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkexcuda.so")
+
+KEX_OK, KEX_ERR_OUT_CAP = 0, -3
+ACCEPT, REJECT = 0, 1
+
+_lib = None
+
+
+class KexError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libkexcuda: %s (%d)" % (msg, code))
+        self.code = code
+
+
+class KexInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "nphases", "nstates", "nclasses", "nregs", "nactions", "max_out_per_byte", "chunk_bytes", "reserved")]
+
+
+EXPORTS = ["kex_load", "kex_free", "kex_info", "kex_run_device", "kex_run_host", "kex_shard_summarize",
+           "kex_shard_walk", "kex_shard_emit", "kex_final_action", "kex_out_bound", "kex_last_launch_count",
+           "kex_set_timing", "kex_last_kernel_ms", "kex_strerror", "kex_last_cuda_error"]
+
+
+def lib():
+    """Load libkexcuda.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            "%s is missing: build it with `python -m kleenexlang_b200.build` "
+            "(there is no CPU fallback for the transducer path)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, sz, u32, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_void_p
+    L.kex_load.argtypes = [ctypes.c_char_p, sz, ctypes.c_int, ctypes.POINTER(vp)]
+    L.kex_load.restype = ctypes.c_int
+    L.kex_free.argtypes = [vp]
+    L.kex_free.restype = None
+    L.kex_info.argtypes = [vp, u32, ctypes.POINTER(KexInfo)]
+    L.kex_run_device.argtypes = [vp, u8p, sz, u8p, sz, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_int),
+                                 ctypes.POINTER(sz), vp]
+    L.kex_run_host.argtypes = [vp, ctypes.c_char_p, sz, u8p, sz, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_int),
+                               ctypes.POINTER(sz)]
+    L.kex_shard_summarize.argtypes = [vp, u8p, sz, ctypes.POINTER(ctypes.c_uint16), vp]
+    L.kex_shard_walk.argtypes = [vp, u32, ctypes.POINTER(u32), ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_uint8), vp]
+    L.kex_shard_emit.argtypes = [vp, u32, sz, u8p, sz, ctypes.POINTER(sz), vp]
+    L.kex_final_action.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(u32),
+                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz)]
+    L.kex_out_bound.argtypes = [vp, sz]
+    L.kex_out_bound.restype = sz
+    L.kex_last_launch_count.argtypes = [vp]
+    L.kex_last_launch_count.restype = u32
+    L.kex_set_timing.argtypes = [vp, ctypes.c_int]
+    L.kex_last_kernel_ms.argtypes = [vp, u32]
+    L.kex_last_kernel_ms.restype = ctypes.c_float
+    L.kex_strerror.argtypes = [ctypes.c_int]
+    L.kex_strerror.restype = ctypes.c_char_p
+    L.kex_last_cuda_error.argtypes = [vp]
+    L.kex_last_cuda_error.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+class CompiledProgram:
+    """A loaded kexprog blob: the CUDA counterpart of a binary produced by
+    `kexc compile` (src/kexc.hs:29-50)."""
+
+    def __init__(self, blob: bytes, device: int = 0):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        self.blob = blob
+        rc = self._L.kex_load(blob, len(blob), device, ctypes.byref(self._h))
+        if rc != KEX_OK:
+            raise KexError(rc, self._L.kex_strerror(rc).decode())
+        self.device = device
+
+    @classmethod
+    def from_kex(cls, src: str, opt: int = 3, device: int = 0):
+        from .kexprog import compile_kex
+        return cls(compile_kex(src, opt), device)
+
+    @classmethod
+    def from_file(cls, path: str, opt: int = 3, device: int = 0):
+        with open(path, encoding="utf-8") as f:
+            return cls.from_kex(f.read(), opt, device)
+
+    def close(self):
+        if self._h:
+            self._L.kex_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != KEX_OK:
+            msg = self._L.kex_strerror(rc).decode()
+            if rc == -2:
+                msg += ": " + self._L.kex_last_cuda_error(self._h).decode()
+            raise KexError(rc, msg)
+
+    def info(self, phase=0):
+        i = KexInfo()
+        self._check(self._L.kex_info(self._h, phase, ctypes.byref(i)))
+        return {n: getattr(i, n) for n, _ in KexInfo._fields_}
+
+    def out_bound(self, n):
+        return self._L.kex_out_bound(self._h, n)
+
+    def set_timing(self, on=True):
+        self._L.kex_set_timing(self._h, 1 if on else 0)
+
+    def kernel_ms(self):
+        return [self._L.kex_last_kernel_ms(self._h, i) for i in range(4)]
+
+    def launch_count(self):
+        return self._L.kex_last_launch_count(self._h)
+
+    def run(self, data: bytes, out_cap=None):
+        """`./bin < data` : returns (status, output bytes, count).  status 0 =
+        accept, 1 = reject with `count` = the reference's
+        "Match error at input symbol <count>!" (C.hs:79-81)."""
+        n = len(data)
+        cap = out_cap if out_cap is not None else max(4 * n + 4096, 4096)
+        while True:
+            buf = ctypes.create_string_buffer(cap)
+            ol, st, fc = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_size_t()
+            rc = self._L.kex_run_host(self._h, data, n, ctypes.cast(buf, ctypes.c_void_p), cap, ctypes.byref(ol),
+                                      ctypes.byref(st), ctypes.byref(fc))
+            if rc == KEX_ERR_OUT_CAP and out_cap is None:
+                cap = ol.value + 4096
+                continue
+            self._check(rc)
+            return st.value, buf.raw[:ol.value], fc.value
+
+    def run_device(self, d_in: int, n: int, d_out: int, out_cap: int, stream: int = 0):
+        """Input and output are device pointers (ints).  Returns
+        (status, out_len, count)."""
+        ol, st, fc = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_size_t()
+        rc = self._L.kex_run_device(self._h, d_in, n, d_out, out_cap, ctypes.byref(ol), ctypes.byref(st),
+                                    ctypes.byref(fc), stream)
+        if rc == KEX_ERR_OUT_CAP:
+            raise KexError(rc, "output buffer too small: need %d bytes" % ol.value)
+        self._check(rc)
+        return st.value, ol.value, fc.value
+
+    # ---- sharded evaluation (one shard per GPU)
+    def shard_summarize(self, d_in: int, n: int, stream: int = 0):
+        q1 = self.info()["nstates"] + 1
+        m = (ctypes.c_uint16 * q1)()
+        self._check(self._L.kex_shard_summarize(self._h, d_in, n, m, stream))
+        return list(m)
+
+    def shard_walk(self, start_state: int, stream: int = 0):
+        r = self.info()["nregs"]
+        end, fail = ctypes.c_uint32(), ctypes.c_size_t()
+        fate = (ctypes.c_uint8 * r)()
+        self._check(self._L.kex_shard_walk(self._h, start_state, ctypes.byref(end), ctypes.byref(fail), fate, stream))
+        fp = fail.value
+        return end.value, (None if fp == ctypes.c_size_t(-1).value else fp), list(fate)
+
+    def shard_emit(self, live_end_mask: int, n_eff: int, d_out: int, out_cap: int, stream: int = 0):
+        ol = ctypes.c_size_t()
+        rc = self._L.kex_shard_emit(self._h, live_end_mask, n_eff, d_out, out_cap, ctypes.byref(ol), stream)
+        if rc == KEX_ERR_OUT_CAP:
+            raise KexError(rc, "output buffer too small: need %d bytes" % ol.value)
+        self._check(rc)
+        return ol.value
+
+    def final_action(self, state: int):
+        acc, mask = ctypes.c_int(), ctypes.c_uint32()
+        tail, tl = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(self._L.kex_final_action(self._h, state, ctypes.byref(acc), ctypes.byref(mask),
+                                             ctypes.byref(tail), ctypes.byref(tl)))
+        data = ctypes.string_at(tail.value, tl.value) if tl.value else b""
+        return bool(acc.value), mask.value, data

@@ -1,0 +1,164 @@
+"""Parity of the CUDA path (through the C ABI of libkexcuda.so) with the CPU
+oracle: reference golden vectors, bundled samples, seeded synthetic inputs,
+reject paths, ragged sizes, the sharded entry points, and size-independent
+properties at larger sizes.  Bit-exact: this is byte/integer work."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import load_vectors, vec_matches, program_source, sample, ROOT
+from kleenexlang_b200 import workloads
+from kleenexlang_b200.frontend.driver import build_ssts
+from kleenexlang_b200.kexprog import compile_kex, UnsupportedProgram
+from oracle.sstbin import oracle_run
+
+pytestmark = pytest.mark.gpu
+VECS = [v for v in load_vectors() if not v["uses_registers"]]
+REF = os.path.join(ROOT, "oracle", "_ref")
+_cache = {}
+
+
+def gpu_prog(src, opt=3):
+    from kleenexlang_b200.runtime import CompiledProgram
+    key = (src, opt)
+    if key not in _cache:
+        _cache[key] = (CompiledProgram(compile_kex(src, opt)), build_ssts(src, opt))
+    return _cache[key]
+
+
+@pytest.mark.parametrize("v", VECS, ids=[v["name"] for v in VECS])
+def test_golden_vectors(v):
+    try:
+        prog, ssts = gpu_prog(v["program"])
+    except UnsupportedProgram:
+        pytest.skip("exceeds device register limit")
+    st, out, cnt = prog.run(v["input"])
+    assert st == 0 and vec_matches(v, out)
+    assert (st, out, cnt if st else 0) == (lambda r: (r[0], r[1], r[2] if r[0] else 0))(oracle_run(ssts, v["input"]))
+
+
+SAMPLES = [("csv2json", "csv_sample.csv"), ("iso_datetime_to_json", "datetime_sample.txt"),
+           ("thousand_sep", "numbers_sample.txt"), ("add-commas", "numbers_sample.txt"),
+           ("apache_log", "apache_sample.log")]
+
+
+@pytest.mark.parametrize("name,fixture", SAMPLES)
+def test_bundled_samples(name, fixture):
+    prog, ssts = gpu_prog(program_source(name))
+    d = sample(fixture)
+    st, out, _ = prog.run(d)
+    est, eout, _ = oracle_run(ssts, d)
+    assert (st, out) == (est, eout)
+
+
+PROGS = ["csv2json", "iso_datetime_to_json", "thousand_sep", "add-commas", "fastq2fasta"]
+
+
+def _check(prog, ssts, d):
+    st, out, cnt = prog.run(d)
+    est, eout, ecnt = oracle_run(ssts, d)
+    assert st == est, (st, est, cnt, ecnt)
+    if st:
+        assert cnt == ecnt
+    assert len(out) == len(eout)
+    assert out == eout
+
+
+@pytest.mark.parametrize("name", PROGS)
+@pytest.mark.parametrize("opt", [0, 3])
+def test_synthetic_vs_oracle(name, opt):
+    prog, ssts = gpu_prog(program_source(name), opt)
+    d = workloads.GENERATORS[name](3 << 20, seed=21).tobytes()
+    _check(prog, ssts, d)
+
+
+@pytest.mark.parametrize("name", PROGS)
+def test_ragged_sizes(name):
+    prog, ssts = gpu_prog(program_source(name))
+    d = workloads.GENERATORS[name](70000, seed=4).tobytes()
+    for n in (0, 1, 2, 31, 32, 33, 4095, 4096, 4097, 8191, 8192, 12289, 65536, len(d)):
+        _check(prog, ssts, d[:n])
+
+
+@pytest.mark.parametrize("name", PROGS)
+def test_reject_paths(name):
+    prog, ssts = gpu_prog(program_source(name))
+    d = workloads.GENERATORS[name](400000, seed=9).tobytes()
+    for pos in (0, 1, 4095, 4096, 100000, 262145, len(d) - 1):
+        bad = d[:pos] + b"\x01" + d[pos + 1:]
+        _check(prog, ssts, bad)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "csv2json")), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("name", PROGS)
+def test_vs_reference_binary(name):
+    prog, _ = gpu_prog(program_source(name))
+    d = workloads.GENERATORS[name](8 << 20, seed=33).tobytes()
+    r = subprocess.run([os.path.join(REF, name)], input=d, capture_output=True)
+    st, out, _ = prog.run(d)
+    assert st == r.returncode
+    assert hashlib.sha256(out).hexdigest() == hashlib.sha256(r.stdout).hexdigest()
+
+
+def test_pipeline_program():
+    src = 'start: p >> a >> b\np := ~/abc/ "a"\na := /./ "b"\nb := /ab/ "c"\n   | ~/[^ab]/ "lol"\n'
+    prog, ssts = gpu_prog(src)
+    assert prog.info()["nphases"] == 3
+    assert prog.run(b"abc") == (0, b"abc", 0)
+    _check(prog, ssts, b"abd")
+
+
+@pytest.mark.parametrize("name", ["csv2json", "iso_datetime_to_json", "thousand_sep"])
+def test_sharded_entry_points(name):
+    """Three shards cut at arbitrary byte positions, stitched with the state
+    and fate maps exactly as the multi-GPU launcher does."""
+    import torch
+    from kleenexlang_b200.runtime import CompiledProgram
+    from kleenexlang_b200.sharding import stitch_states, stitch_live
+    blob = compile_kex(program_source(name))
+    ssts = build_ssts(program_source(name))
+    d = workloads.GENERATORS[name](600000, seed=2).tobytes()
+    cuts = [0, 199993, 400016, len(d)]       # multiples of 16 not required between ranks; each shard is its own buffer
+    shards = [d[cuts[i]:cuts[i + 1]] for i in range(3)]
+    progs = [CompiledProgram(blob) for _ in shards]
+    bufs = [torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda() for s in shards]
+    maps = [p.shard_summarize(b.data_ptr(), b.numel()) for p, b in zip(progs, bufs)]
+    init = 0
+    info = progs[0].info()
+    starts = stitch_states(maps, build_ssts(program_source(name))[0].initial)
+    walks = [p.shard_walk(s) for p, s in zip(progs, starts)]
+    assert all(w[1] is None for w in walks)
+    acc, mask, tail = progs[-1].final_action(walks[-1][0])
+    assert acc
+    lives = stitch_live([w[2] for w in walks], mask)
+    outs = []
+    for p, b, live in zip(progs, bufs, lives):
+        o = torch.empty(4 * b.numel() + 64, dtype=torch.uint8, device="cuda")
+        n = p.shard_emit(live, b.numel(), o.data_ptr(), o.numel())
+        outs.append(bytes(o[:n].cpu().numpy()))
+    got = b"".join(outs) + tail
+    assert (0, got) == oracle_run(ssts, d)[:2]
+
+
+def test_large_properties_csv2json():
+    """256 MiB: tiling the input tiles the output (record* grammar), and the
+    output length is input + 127 bytes per row."""
+    import torch
+    prog, ssts = gpu_prog(program_source("csv2json"))
+    block = workloads.gen_csv(4 << 20, seed=77)
+    reps = 64
+    rows = int((block == 10).sum())
+    dev_block = torch.from_numpy(block).cuda()
+    big = dev_block.repeat(reps)
+    out = torch.empty(int(big.numel() * 2.2), dtype=torch.uint8, device="cuda")
+    st, olen, _ = prog.run_device(big.data_ptr(), big.numel(), out.data_ptr(), out.numel())
+    assert st == 0 and olen == big.numel() + 127 * rows * reps
+    est, eout, _ = oracle_run(ssts, block.tobytes())
+    per = len(eout)
+    assert olen == per * reps
+    o = out[:olen].view(reps, per)
+    ref = torch.frombuffer(bytearray(eout), dtype=torch.uint8).cuda()
+    assert bool((o == ref[None, :]).all())

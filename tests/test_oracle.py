@@ -1,0 +1,65 @@
+"""The CPU oracle (oracle/kex_oracle.c) pinned against the reference's golden
+vectors, the cross-tool digests, and -- when they have been built -- the
+reference's own compiled binaries (oracle/_ref: emitted C + verbatim crt.c)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import load_vectors, vec_matches, program_source, sample, GOLDEN, ROOT
+from kleenexlang_b200.frontend.driver import build_ssts
+from kleenexlang_b200 import workloads
+from oracle.sstbin import oracle_run
+
+VECS = [v for v in load_vectors() if not v["uses_registers"]]
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+@pytest.mark.parametrize("opt", [0, 3])
+@pytest.mark.parametrize("v", VECS, ids=[v["name"] for v in VECS])
+def test_oracle_golden(v, opt):
+    st, out, _ = oracle_run(build_ssts(v["program"], opt), v["input"])
+    assert st == 0 and vec_matches(v, out)
+
+
+def test_oracle_cross_tool():
+    cross = json.load(open(os.path.join(GOLDEN, "cross_tool.json")))
+    for prog, key in (("iso_datetime_to_json", "perl_sha256"), ("iso_datetime_to_json", "python_sha256"),
+                      ("thousand_sep", "perl_sha256"), ("apache_log", "perl_sha256_normalised")):
+        st, out, _ = oracle_run(build_ssts(program_source(prog)), sample(cross[prog]["input"]))
+        assert st == 0 and hashlib.sha256(out).hexdigest() == cross[prog][key], (prog, key)
+    st, out, _ = oracle_run(build_ssts(program_source("csv2json")), sample("csv_sample.csv"))
+    assert st == 0 and len(out) == cross["csv2json"]["output_len"]
+    assert out.decode().startswith(cross["csv2json"]["first_record"])
+
+
+def _ref(name, data):
+    r = subprocess.run([os.path.join(REF, name)], input=data, capture_output=True)
+    return r.returncode, r.stdout, r.stderr
+
+
+CASES = [("csv2json", "csv2json"), ("iso_datetime_to_json", "iso_datetime_to_json"), ("thousand_sep", "thousand_sep"),
+         ("add-commas", "add-commas"), ("fastq2fasta", "fastq2fasta")]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "csv2json")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("prog,gen", CASES)
+def test_oracle_vs_reference_binary(prog, gen):
+    ssts = build_ssts(program_source(prog))
+    data = workloads.GENERATORS[gen](200000, seed=11).tobytes()
+    # accept, reject mid-stream (after several 16 KiB flushes), reject at end of input, empty input
+    bad = data[:150001] + b"\x01" + data[150001:]
+    for d in (data, bad, data[:-1] if prog != "add-commas" else data + b"1", b""):
+        st, out, cnt = oracle_run(ssts, d)
+        rc, ro, err = _ref(prog, d)
+        assert (st, out) == (rc, ro)
+        if rc:
+            assert ("symbol %d!" % cnt).encode() in err
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "apache_log")), reason="oracle/_ref not built")
+def test_oracle_vs_reference_binary_apache():
+    d = sample("apache_sample.log")
+    assert oracle_run(build_ssts(program_source("apache_log")), d)[:2] == _ref("apache_log", d)[:2]

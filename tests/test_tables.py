@@ -1,0 +1,61 @@
+"""Device-table construction (kexprog) checked on the CPU: the executable
+model of the CUDA algorithm (tests/gpu_model.py), run over the same tables the
+blob is serialised from, must agree with the C oracle for every chunking."""
+import pytest
+
+from conftest import load_vectors, program_source, sample
+from gpu_model import run_model
+from kleenexlang_b200 import workloads
+from kleenexlang_b200.frontend.driver import build_ssts
+from kleenexlang_b200.kexprog import build_phase, compile_kex, serialize_pipeline, UnsupportedProgram
+from oracle.sstbin import oracle_run
+
+VECS = [v for v in load_vectors() if not v["uses_registers"]]
+
+
+def _model_pipeline(tabs, data, chunk):
+    st, cnt = 0, 0
+    for t in tabs:
+        ok, data, cnt = run_model(t, data, chunk)
+        st = 0 if ok else 1
+    return st, data, cnt
+
+
+@pytest.mark.parametrize("v", VECS, ids=[v["name"] for v in VECS])
+def test_model_golden(v):
+    ssts = build_ssts(v["program"], 3)
+    try:
+        tabs = [build_phase(s) for s in ssts]
+    except UnsupportedProgram:
+        pytest.skip("exceeds device register limit")
+    for chunk in (1, 5, 64):
+        assert _model_pipeline(tabs, v["input"], chunk) == oracle_run(ssts, v["input"])
+
+
+@pytest.mark.parametrize("prog", ["csv2json", "iso_datetime_to_json", "thousand_sep", "add-commas", "fastq2fasta"])
+@pytest.mark.parametrize("opt", [0, 3])
+def test_model_workloads(prog, opt):
+    ssts = build_ssts(program_source(prog), opt)
+    tabs = [build_phase(s) for s in ssts]
+    data = workloads.GENERATORS[prog](3000, seed=5).tobytes()
+    bad = data[:1700] + b"\x01" + data[1700:]
+    for d in (data, bad, data[:-3], b""):
+        for chunk in (3, 32, 4096):
+            assert _model_pipeline(tabs, d, chunk) == oracle_run(ssts, d), (prog, opt, chunk, len(d))
+
+
+def test_model_apache():
+    ssts = build_ssts(program_source("apache_log"), 3)
+    tabs = [build_phase(s) for s in ssts]
+    d = sample("apache_sample.log")[:6000]
+    d = d[:d.rfind(b"\n") + 1]
+    assert _model_pipeline(tabs, d, 50) == oracle_run(ssts, d)
+
+
+def test_blob_layout():
+    blob = compile_kex(program_source("csv2json"))
+    assert blob[:4] == b"KEXL" and len(blob) % 16 == 0
+    t = build_phase(build_ssts(program_source("csv2json"))[0])
+    assert (t.Q, t.C, t.R) == (27, 5, 5)
+    assert len(serialize_pipeline([t])) == len(blob)
+    assert build_phase(build_ssts(program_source("fastq2fasta"))[0]).R == 1
