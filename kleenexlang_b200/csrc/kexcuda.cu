@@ -783,18 +783,13 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
     int rc = ((size_t)off + len > blob_len) ? KEX_ERR_BAD_BLOB : load_phase(p, b + off, len, p->phases[i]);
     if (rc != KEX_OK) { kex_free(p); return rc; }
   }
-  size_t mx_walk = 0, mx_maps = 0, mx_e0 = 0, mx_e1 = 0, mx_e4 = 0;
-  for (auto &ph : p->phases) {
-    if (ph.smem_walk > mx_walk) mx_walk = ph.smem_walk;
-    if (ph.smem_maps > mx_maps) mx_maps = ph.smem_maps;
-    size_t &m = (ph.mask_bytes == 0) ? mx_e0 : (ph.mask_bytes == 1 ? mx_e1 : mx_e4);
-    if (ph.smem_emit > m) m = ph.smem_emit;
-  }
-  cudaFuncSetAttribute(k_chunk_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_maps);
-  cudaFuncSetAttribute(k_true_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_walk);
-  if (mx_e0) cudaFuncSetAttribute(k_emit<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_e0);
-  if (mx_e1) cudaFuncSetAttribute(k_emit<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_e1);
-  if (mx_e4) cudaFuncSetAttribute(k_emit<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx_e4);
+  // the attribute is per function, not per handle: always allow the device maximum
+  const int mx = 200 * 1024;
+  cudaFuncSetAttribute(k_chunk_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_true_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_emit<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_emit<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_emit<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   if (cudaMallocHost((void **)&p->res_host, sizeof(RunResult)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&p->ev[i]);
   p->ev_ok = true;

@@ -136,7 +136,7 @@ def test_sharded_entry_points(name):
     lives = stitch_live([w[2] for w in walks], mask)
     outs = []
     for p, b, live in zip(progs, bufs, lives):
-        o = torch.empty(4 * b.numel() + 64, dtype=torch.uint8, device="cuda")
+        o = torch.empty(6 * b.numel() + 64, dtype=torch.uint8, device="cuda")
         n = p.shard_emit(live, b.numel(), o.data_ptr(), o.numel())
         outs.append(bytes(o[:n].cpu().numpy()))
     got = b"".join(outs) + tail
