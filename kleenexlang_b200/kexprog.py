@@ -253,7 +253,7 @@ def build_phase(sst) -> PhaseTables:
     return t
 
 
-def serialize_phase(t: PhaseTables) -> bytes:
+def serialize_phase(t: PhaseTables, with_fast: bool = True) -> bytes:
     piece_off = []
     flat = []
     for ps in t.pieces:
@@ -290,14 +290,26 @@ def serialize_phase(t: PhaseTables) -> bytes:
     pad = (-off) % 16
     body += b"\0" * pad
     off += pad
+    # optional fast section (monoid tables, fasttab.py); programs that exceed
+    # its limits run on the generic kernels
+    fast_off, fast_len = 0, 0
+    if with_fast:
+        from . import fasttab
+        try:
+            fb = fasttab.serialize_fast(t, fasttab.build_fast(t))
+            fast_off, fast_len = off, len(fb)
+            body += fb
+            off += len(fb)
+        except fasttab.Ineligible:
+            pass
     hdr = [MAGIC_PHASE, VERSION, t.Q, t.C, t.R, t.A, len(flat), len(t.consts), t.init,
-           t.max_out_per_byte] + offs + [off]
+           t.max_out_per_byte] + offs + [off, fast_off, fast_len]
     hdr += [0] * (nhdr - len(hdr))
     return struct.pack("<%dI" % nhdr, *hdr) + bytes(body)
 
 
-def serialize_pipeline(phases) -> bytes:
-    blobs = [serialize_phase(t) for t in phases]
+def serialize_pipeline(phases, with_fast: bool = True) -> bytes:
+    blobs = [serialize_phase(t, with_fast) for t in phases]
     n = len(blobs)
     hdr_words = 4 + 2 * n
     hdr_size = (hdr_words * 4 + 15) // 16 * 16
@@ -311,7 +323,7 @@ def serialize_pipeline(phases) -> bytes:
     return hdr + b"".join(blobs)
 
 
-def compile_kex(src: str, opt: int = 3) -> bytes:
+def compile_kex(src: str, opt: int = 3, with_fast: bool = True) -> bytes:
     """`.kex` source -> kexprog blob (the CUDA counterpart of
     `kexc compile --act=false --la=false`)."""
     from .frontend.driver import build_ssts
@@ -326,4 +338,4 @@ def compile_kex(src: str, opt: int = 3) -> bytes:
             # register; the unoptimised SST always has the required shape
             s0 = build_ssts(src, 0)[len(phases)]
             phases.append(build_phase(s0))
-    return serialize_pipeline(phases)
+    return serialize_pipeline(phases, with_fast)

