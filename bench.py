@@ -215,25 +215,25 @@ def main():
         assert st == 0 and olen == expect_out, (st, olen, expect_out)
         return prog.launch_count()
 
-    q1, nregs = info["nstates"] + 1, info["nregs"]
+    q1, nseam = info["nstates"] + 1, prog.seam_bytes()
     init_state = 0
 
     def step_sharded():
-        # K1+K2 locally, all-gather the state maps, K3 locally, all-gather the
-        # fate maps + end states, K4+K5 locally; output stays sharded in rank order
+        # state maps locally, all-gather them, seams locally, all-gather the seam
+        # summaries + end-of-input code, emit locally; output stays sharded in rank order
         m = prog.shard_summarize(d_in.data_ptr(), n, stream)
         t = torch.tensor(m, dtype=torch.int32, device="cuda")
         allm = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(allm, t)
         starts = stitch_states([x.tolist() for x in allm], init_state)
-        end, fail, fate = prog.shard_walk(starts[rank], stream)
+        end, fail, seam = prog.shard_walk(starts[rank], stream)
         assert fail is None
-        acc, mask, tail = prog.final_action(end)
-        t2 = torch.tensor(fate + [mask if acc else 0], dtype=torch.int32, device="cuda")
+        acc, code, tail = prog.final_action(end)
+        t2 = torch.tensor(list(seam) + [code if acc else 0], dtype=torch.int32, device="cuda")
         allf = [torch.empty_like(t2) for _ in range(world)]
         dist.all_gather(allf, t2)
         fl = [x.tolist() for x in allf]
-        lives = stitch_live([f[:nregs] for f in fl], fl[-1][nregs])
+        lives = stitch_live(prog, [bytes(f[:nseam]) for f in fl], fl[-1][nseam])
         olen = prog.shard_emit(lives[rank], n, d_out.data_ptr(), d_out.numel(), stream)
         assert olen == expect_out, (olen, expect_out)
         return prog.launch_count()      # cumulative since shard_summarize
@@ -327,10 +327,10 @@ def main():
             ach = ALGO_BYTES_PER_IN_measured(n, expect_out) / (emit_ms / 1000.0) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": (EMIT_TRAFFIC_PER_IN * n) if EMIT_TRAFFIC_PER_IN else None,
-                                "kernel": "k_emit", "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % how,
+                                "kernel": "k_emit_fast", "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % how,
                                 "algorithmic_bytes_per_launch": n + expect_out,
-                                "kernel_ms": {"k_chunk_maps": kms[0] / args.steps, "k_true_walk": kms[1] / args.steps,
-                                              "k_emit": emit_ms, "all_device_work": kms[3] / args.steps},
+                                "kernel_ms": {"k_fwd_monoid": kms[0] / args.steps, "k_seams": kms[1] / args.steps,
+                                              "k_emit_fast": emit_ms, "all_device_work": kms[3] / args.steps},
                                 "pipeline_frac": (n + expect_out) / (ms_per_step / 1000.0) / 1e9 / peak}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()

@@ -48,7 +48,7 @@ typedef struct {
   uint32_t nactions;       /* distinct register-update actions, phase 0          */
   uint32_t max_out_per_byte; /* worst-case output bytes per input byte, phase 0  */
   uint32_t chunk_bytes;    /* bytes one device chunk covers                      */
-  uint32_t reserved;
+  uint32_t monoid_kernels; /* 1: phase 0 runs on the monoid kernels, 0: generic   */
 } kex_info_t;
 
 /* Replaces the emit+cc step of compileProgram (C.hs:529-568) and `init()`
@@ -62,8 +62,8 @@ void kex_free(kex_program *p);
 int kex_info(const kex_program *p, uint32_t phase, kex_info_t *info);
 
 /* Replaces `run(phase)` for every phase of the pipeline (crt/crt.c:356-364,
- * 414-455) with input and output resident in device memory.  `d_in` must be
- * 16-byte aligned.  On KEX_OK: *status is KEX_ACCEPT or KEX_REJECT, *out_len
+ * 414-455) with input and output resident in device memory.  `d_in` and `d_out`
+ * must be 16-byte aligned.  On KEX_OK: *status is KEX_ACCEPT or KEX_REJECT, *out_len
  * the bytes written to d_out, *fail_count the reference's `count` (bytes
  * consumed by completed transitions, C.hs:79-81) when rejecting.  A rejecting
  * run leaves exactly the whole 16 KiB flushes the C runtime would have
@@ -80,30 +80,38 @@ int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n,
                  int *status, size_t *fail_count);
 
 /* ---- sharded evaluation (one shard per GPU; single-phase programs) --------
- * The transducer run is a prefix computation over (state map, register fate
- * map).  A shard is evaluated in three steps so that ranks can exchange the
- * two small summaries (all-gather) between them:
+ * The transducer run is a prefix computation over the SST's transition monoid
+ * (src/KMC/SymbolicSST.hs:122-136): forward over the state maps, backward
+ * over which registers still reach the output stream.  A shard is evaluated
+ * in three steps so that ranks can exchange the two small summaries (one
+ * all-gather each) between them:
  *
  *   kex_shard_summarize : state map of the shard for every start state
  *   kex_shard_walk      : given the true start state -> end state, first
- *                         failure, fate map of the registers over the shard
- *   kex_shard_emit      : given which registers are live at the shard's end
- *                         -> write the shard's output bytes
+ *                         failure, the shard's seam summary (opaque,
+ *                         kex_seam_bytes() bytes: how liveness of the
+ *                         registers at the shard's end maps to its start)
+ *   kex_stitch_live     : all seam summaries + the end-of-input action ->
+ *                         seam code at the end of every shard (host only)
+ *   kex_shard_emit      : given its seam code -> write the shard's output
  *
- * State maps have nstates+1 uint16 entries (the last is the FAIL sink), fate
- * maps nregs uint8 entries (0 = flushed to the stream, 0xFF = dropped).     */
+ * State maps have nstates+1 uint16 entries (the last is the FAIL sink).     */
 int kex_shard_summarize(kex_program *p, const uint8_t *d_in, size_t n,
                         uint16_t *h_state_map, void *stream);
+size_t kex_seam_bytes(const kex_program *p);
 int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *end_state,
-                   size_t *fail_pos /* (size_t)-1 if none */, uint8_t *h_fate_map,
+                   size_t *fail_pos /* (size_t)-1 if none */, uint8_t *h_seam,
                    void *stream);
-int kex_shard_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff,
+int kex_stitch_live(const kex_program *p, const uint8_t *seams, size_t nshards,
+                    uint32_t final_code, uint32_t *codes);
+int kex_shard_emit(kex_program *p, uint32_t seam_code, size_t n_eff,
                    uint8_t *d_out, size_t out_cap, size_t *out_len, void *stream);
 
-/* Final-state action: is `state` accepting, which registers does the end-of-
- * input action flush (bit r), and its literal tail (SSTCompiler.hs:147-154). */
+/* Final-state action: is `state` accepting, the seam code of the end-of-input
+ * action (which registers it flushes), and its literal tail
+ * (SSTCompiler.hs:147-154). */
 int kex_final_action(const kex_program *p, uint32_t state, int *accepting,
-                     uint32_t *flush_mask, const uint8_t **tail, size_t *tail_len);
+                     uint32_t *seam_code, const uint8_t **tail, size_t *tail_len);
 
 /* Upper bound on the output size for n input bytes (all phases). */
 size_t kex_out_bound(const kex_program *p, size_t n);

@@ -613,6 +613,8 @@ __global__ void k_copy_tail(const uint8_t *__restrict__ src, uint32_t len, uint8
   for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
 }
 
+#include "kex_fast.cuh"
+
 // =================================================================== host
 struct PhaseHost {
   PhaseDev dev;
@@ -625,6 +627,15 @@ struct PhaseHost {
   void *d_extra = nullptr;           // derived tables (nextpm, actinfo, img_*)
   size_t smem_walk = 0, smem_maps = 0, smem_emit = 0;
   int mask_bytes = 0;
+  // monoid kernels (fast section of the blob); absent -> generic kernels
+  bool fast = false;
+  FastDev fdev;
+  std::vector<uint8_t> lam_final;     // [Q+1] live-set index flushed at end of input, 0xFF = reject
+  std::vector<uint32_t> lam_masks;    // [NL] register mask of every live set
+  size_t smem_fm = 0, smem_ef_tables = 0;
+  uint32_t stage_bytes = 12288;       // emit staging window; grows with the observed out/in ratio
+  int ef_ctas_per_sm = 0;
+  uint32_t ef_stage_cfg = 0;          // stage_bytes the occupancy was computed for
 };
 
 struct Buf {
@@ -644,6 +655,9 @@ struct kex_program {
   // scratch (grow-only)
   Buf maps[8], starts[8], fates[8], lives[8];
   Buf samples, pend, resolved, fail, outlen, outoff, bsum, res_dev, inter[2], hostio_in, hostio_out;
+  Buf bmaps[8], lams[8], desc, ctl;
+  FastCtl *ctl_host = nullptr;
+  int num_sms = 0;
   RunResult *res_host = nullptr;
   // shard state between the three shard calls
   const uint8_t *sh_in = nullptr;
@@ -677,6 +691,73 @@ static uint32_t rd32(const uint8_t *b, size_t off) {
   uint32_t v;
   memcpy(&v, b + off, 4);
   return v;
+}
+
+
+// Fast section (fasttab.py): monoid tables.  Malformed -> KEX_ERR_BAD_BLOB;
+// tables too large for shared memory -> the phase stays on the generic kernels.
+static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
+  const uint32_t fo = rd32(b, 76), fl = rd32(b, 80);
+  if (fo == 0 || getenv("KEX_FORCE_GENERIC")) return KEX_OK;
+  if ((size_t)fo + fl > len || fl < 128) return KEX_ERR_BAD_BLOB;
+  const uint8_t *f = b + fo;
+  if (rd32(f, 0) != 0x4658454Bu || rd32(f, 4) != 1u || rd32(f, 40) != fl) return KEX_ERR_BAD_BLOB;
+  const uint32_t Q1 = ph.dev.Q + 1, C = ph.dev.C, A = ph.dev.A;
+  const uint32_t NM = rd32(f, 8), NL = rd32(f, 16), NG = rd32(f, 20), NB = rd32(f, 24), NT = rd32(f, 28),
+                 pool_len = rd32(f, 32), max_emit = rd32(f, 36);
+  if (rd32(f, 12) != Q1 || NM == 0 || NL == 0 || NL > 64 || NG == 0 || NG > 255 || NB == 0 || NB > 255 || NT > 255 ||
+      A > 255 || C > 63 || (size_t)NM * C > 65535 || (size_t)NL * A * 4 > 65535)
+    return KEX_ERR_BAD_BLOB;
+  uint32_t off[12];
+  for (int i = 0; i < 12; ++i) off[i] = rd32(f, 44 + 4 * i);
+  const size_t need[12] = {2ull * NM * C, 2ull * NM * Q1, 4ull * Q1 * C, 4ull * NL * A, Q1,       (size_t)NB * NG,
+                           (size_t)NB * NB, (size_t)NB * NL, NB,          8ull * NT,   pool_len, 4ull * NL};
+  for (int i = 0; i < 12; ++i)
+    if ((size_t)off[i] + need[i] > fl) return KEX_ERR_BAD_BLOB;
+  const uint16_t *mulF = (const uint16_t *)(f + off[0]), *applyF = (const uint16_t *)(f + off[1]);
+  const uint32_t *trans2 = (const uint32_t *)(f + off[2]), *BE = (const uint32_t *)(f + off[3]);
+  for (size_t i = 0; i < (size_t)NM * C; ++i) if (mulF[i] >= NM) return KEX_ERR_BAD_BLOB;
+  for (size_t i = 0; i < (size_t)NM * Q1; ++i) if (applyF[i] >= Q1) return KEX_ERR_BAD_BLOB;
+  for (uint32_t i = 0; i < Q1 * C; ++i)
+    if ((trans2[i] & 0xFFFFu) >= Q1 || ((trans2[i] >> 16) & 0xFFu) >= A || (trans2[i] >> 24) >= NG) return KEX_ERR_BAD_BLOB;
+  const uint32_t *tplinfo = (const uint32_t *)(f + off[9]);
+  for (uint32_t i = 0; i < NL * A; ++i) {
+    const uint32_t e = BE[i];
+    if ((e & 0xFFFCu) % (4 * A) != 0 || (e & 0xFFFCu) / (4 * A) >= NL) return KEX_ERR_BAD_BLOB;
+    if ((e & 2u) && ((e >> 24) >= NT || (tplinfo[2 * (e >> 24)] >> 16) != ((e >> 16) & 0xFFu))) return KEX_ERR_BAD_BLOB;
+  }
+  for (uint32_t i = 0; i < NT; ++i)
+    if ((tplinfo[2 * i] & 0xFFFFu) + (tplinfo[2 * i] >> 16) > pool_len) return KEX_ERR_BAD_BLOB;
+  for (size_t i = 0; i < (size_t)NB * NG; ++i) if (f[off[5] + i] >= NB) return KEX_ERR_BAD_BLOB;
+  for (size_t i = 0; i < (size_t)NB * NB; ++i) if (f[off[6] + i] >= NB) return KEX_ERR_BAD_BLOB;
+  for (size_t i = 0; i < (size_t)NB * NL; ++i) if (f[off[7] + i] >= NL) return KEX_ERR_BAD_BLOB;
+  ph.lam_final.assign(f + off[4], f + off[4] + Q1);
+  for (uint8_t x : ph.lam_final) if (x != 0xFF && x >= NL) return KEX_ERR_BAD_BLOB;
+  ph.lam_masks.assign((const uint32_t *)(f + off[11]), (const uint32_t *)(f + off[11]) + NL);
+
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t tables = al(4ull * Q1 * C) + al(4ull * NL * A) + al(8ull * NT) + 256 + al((size_t)NB * NG) +
+                        al((size_t)NB * NB) + al((size_t)NB * NL) + al(pool_len);
+  ph.smem_fm = 256 + al(2ull * NM * C);
+  if (tables > 40 * 1024 || ph.smem_fm > 160 * 1024) return KEX_OK;      // generic kernels
+  const uint8_t *db = (const uint8_t *)ph.d_blob + fo;                  // the blob is already on the device
+  FastDev &d = ph.fdev;
+  d.NM = NM; d.NL = NL; d.NG = NG; d.NB = NB; d.NT = NT; d.pool_len = pool_len; d.max_emit = max_emit;
+  d.tbl_bytes = (uint32_t)tables;
+  d.mulF = (const uint16_t *)(db + off[0]);
+  d.applyF = (const uint16_t *)(db + off[1]);
+  d.trans2 = (const uint32_t *)(db + off[2]);
+  d.BE = (const uint32_t *)(db + off[3]);
+  d.lam_final = db + off[4];
+  d.mulB = db + off[5];
+  d.compB = db + off[6];
+  d.applyB = db + off[7];
+  d.constB = db + off[8];
+  d.tplinfo = (const uint32_t *)(db + off[9]);
+  d.pool = db + off[10];
+  ph.smem_ef_tables = tables;
+  ph.fast = true;
+  return KEX_OK;
 }
 
 static int load_phase(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
@@ -764,7 +845,7 @@ static int load_phase(kex_program *p, const uint8_t *b, size_t len, PhaseHost &p
   ph.smem_emit = KEX_CHUNK + KEX_STAGE + 32 + (size_t)KEX_CHUNK * 2 + (size_t)KEX_CHUNK * ph.mask_bytes +
                  (ph.mask_bytes ? 2u * KEX_NT * 32u : 0u) + (size_t)Q1 * C * 4 + (size_t)A * 4 + 256;
   if (ph.smem_emit > 200 * 1024 || ph.smem_walk > 200 * 1024) return KEX_ERR_UNSUPPORTED;
-  return KEX_OK;
+  return load_fast(p, b, len, ph);
 }
 
 extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_program **out) {
@@ -790,6 +871,11 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
   cudaFuncSetAttribute(k_emit<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_emit<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_emit<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_fwd_monoid, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_emit_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_emit_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (cudaMallocHost((void **)&p->ctl_host, sizeof(FastCtl)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
   if (cudaMallocHost((void **)&p->res_host, sizeof(RunResult)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&p->ev[i]);
   p->ev_ok = true;
@@ -803,7 +889,9 @@ extern "C" void kex_free(kex_program *p) {
   for (auto &ph : p->phases) { cudaFree(ph.d_blob); cudaFree(ph.d_extra); }
   for (int i = 0; i < 8; ++i) { cudaFree(p->maps[i].p); cudaFree(p->starts[i].p); cudaFree(p->fates[i].p); cudaFree(p->lives[i].p); }
   Buf *bs[] = {&p->samples, &p->pend, &p->resolved, &p->fail, &p->outlen, &p->outoff, &p->bsum, &p->res_dev,
-               &p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out};
+               &p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out, &p->desc, &p->ctl};
+  for (int i = 0; i < 8; ++i) { cudaFree(p->bmaps[i].p); cudaFree(p->lams[i].p); }
+  if (p->ctl_host) cudaFreeHost(p->ctl_host);
   for (Buf *b : bs) cudaFree(b->p);
   if (p->res_host) cudaFreeHost(p->res_host);
   if (p->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(p->ev[i]);
@@ -815,18 +903,25 @@ extern "C" int kex_info(const kex_program *p, uint32_t phase, kex_info_t *info) 
   const PhaseDev &d = p->phases[phase].dev;
   info->nphases = (uint32_t)p->phases.size();
   info->nstates = d.Q; info->nclasses = d.C; info->nregs = d.R; info->nactions = d.A;
-  info->max_out_per_byte = d.max_out; info->chunk_bytes = KEX_CHUNK; info->reserved = 0;
+  info->max_out_per_byte = d.max_out; info->chunk_bytes = KEX_CHUNK;
+  info->monoid_kernels = p->phases[phase].fast ? 1u : 0u;
   return KEX_OK;
 }
 
-extern "C" int kex_final_action(const kex_program *p, uint32_t state, int *accepting, uint32_t *flush_mask,
+static uint32_t final_code(const PhaseHost &ph, uint32_t state) {
+  const int32_t a = ph.fin[state];
+  if (a < 0) return 0u;
+  return ph.fast ? (uint32_t)ph.lam_final[state] : ph.acts[a].flush_mask;
+}
+
+extern "C" int kex_final_action(const kex_program *p, uint32_t state, int *accepting, uint32_t *seam_code,
                                 const uint8_t **tail, size_t *tail_len) {
   if (!p) return KEX_ERR_ARG;
   const PhaseHost &ph = p->phases[p->sh_phase];
   if (state > ph.dev.Q) return KEX_ERR_ARG;
   const int32_t a = ph.fin[state];
   if (accepting) *accepting = a >= 0;
-  if (flush_mask) *flush_mask = a >= 0 ? ph.acts[a].flush_mask : 0u;
+  if (seam_code) *seam_code = final_code(ph, state);
   // the tail is the concatenation of the action's constant pieces (all target the stream)
   static thread_local std::vector<uint8_t> buf;
   buf.clear();
@@ -868,8 +963,14 @@ extern "C" const char *kex_strerror(int code) {
 }
 
 // ---------------------------------------------------------------- shard steps
+static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, cudaStream_t st);
+static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st);
+static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t *d_out, size_t out_cap, size_t *out_len,
+                        cudaStream_t st);
+
 static int do_summarize(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, cudaStream_t st) {
   PhaseHost &ph = p->phases[phase];
+  if (ph.fast) return do_summarize_fast(p, phase, d_in, n, st);
   const PhaseDev &P = ph.dev;
   const uint32_t Q1 = P.Q + 1;
   if (((uintptr_t)d_in & 15u) != 0) return KEX_ERR_ARG;
@@ -908,6 +1009,7 @@ static int do_summarize(kex_program *p, uint32_t phase, const uint8_t *d_in, siz
 
 static int do_walk(kex_program *p, uint32_t start_state, cudaStream_t st) {
   PhaseHost &ph = p->phases[p->sh_phase];
+  if (ph.fast) return do_walk_fast(p, start_state, st);
   const PhaseDev &P = ph.dev;
   const uint32_t Q1 = P.Q + 1, R = P.R;
   const size_t nchunks = p->sh_nchunks, n = p->sh_n;
@@ -968,6 +1070,7 @@ static int do_fate_up(kex_program *p, size_t nchunks_eff, uint8_t *h_fate, cudaS
 static int do_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff, uint8_t *d_out, size_t out_cap,
                    size_t *out_len, cudaStream_t st) {
   PhaseHost &ph = p->phases[p->sh_phase];
+  if (ph.fast) return do_emit_fast(p, live_end_mask, n_eff, d_out, out_cap, out_len, st);
   const PhaseDev &P = ph.dev;
   const uint32_t R = P.R;
   *out_len = 0;
@@ -1032,6 +1135,163 @@ static int do_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff, uint8_t
   return KEX_OK;
 }
 
+
+// ------------------------------------------------------- monoid-kernel steps
+static void level_counts(size_t nchunks, size_t *cnt, int *nl) {
+  int n = 0;
+  size_t c = nchunks;
+  while (true) { cnt[n++] = c; if (c <= 1) break; c = (c + KEX_FANIN - 1) / KEX_FANIN; }
+  *nl = n;
+}
+
+static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, cudaStream_t st) {
+  PhaseHost &ph = p->phases[phase];
+  const PhaseDev &P = ph.dev;
+  const uint32_t Q1 = P.Q + 1;
+  if (((uintptr_t)d_in & 15u) != 0) return KEX_ERR_ARG;
+  p->sh_in = d_in; p->sh_n = n; p->sh_phase = phase;
+  const size_t nchunks = (n + KEX_CHUNK - 1) / KEX_CHUNK;
+  p->sh_nchunks = nchunks;
+  level_counts(nchunks, p->lvl_count, &p->nlevels);
+  int rc;
+  for (int l = 0; l < p->nlevels; ++l) {
+    if ((rc = ensure(p, p->maps[l], p->lvl_count[l] * Q1 * sizeof(uint16_t)))) return rc;
+    if ((rc = ensure(p, p->starts[l], p->lvl_count[l] * sizeof(uint16_t)))) return rc;
+  }
+  if ((rc = ensure(p, p->res_dev, sizeof(RunResult)))) return rc;
+  if ((rc = ensure(p, p->samples, nchunks * KEX_NT * sizeof(uint16_t)))) return rc;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], st));
+  k_fwd_monoid<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_fm, st>>>(P, ph.fdev, d_in, n, nchunks,
+                                                                          (uint16_t *)p->samples.p, (uint16_t *)p->maps[0].p);
+  p->launches++;
+  if (p->timing) CK(cudaEventRecord(p->ev[1], st));
+  const unsigned bt = Q1 < 32 ? 32 : (Q1 > 256 ? 256 : ((Q1 + 31) / 32 * 32));
+  for (int l = 1; l < p->nlevels; ++l) {
+    k_compose<uint16_t, false><<<(unsigned)p->lvl_count[l], bt, 0, st>>>((const uint16_t *)p->maps[l - 1].p, p->lvl_count[l - 1],
+                                                                       (uint16_t *)p->maps[l].p, Q1);
+    p->launches++;
+  }
+  CK(cudaGetLastError());
+  return KEX_OK;
+}
+
+static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st) {
+  PhaseHost &ph = p->phases[p->sh_phase];
+  const PhaseDev &P = ph.dev;
+  const uint32_t Q1 = P.Q + 1, NL = ph.fdev.NL;
+  const size_t nchunks = p->sh_nchunks, n = p->sh_n;
+  const int top = p->nlevels - 1;
+  k_set_u16<<<1, 1, 0, st>>>((uint16_t *)p->starts[top].p, start_state);
+  p->launches++;
+  for (int l = top; l >= 1; --l) {
+    const size_t np = p->lvl_count[l];
+    k_push_states<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const uint16_t *)p->maps[l - 1].p, p->lvl_count[l - 1],
+                                                                (const uint16_t *)p->starts[l].p, np,
+                                                                (uint16_t *)p->starts[l - 1].p, Q1);
+    p->launches++;
+  }
+  int rc;
+  if ((rc = ensure(p, p->fail, nchunks * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(p, p->bmaps[0], nchunks * NL))) return rc;
+  if (p->timing) CK(cudaEventRecord(p->ev[2], st));
+  k_seams<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(P, ph.fdev, p->sh_in, n, nchunks, (const uint16_t *)p->starts[0].p,
+                                                            (const uint16_t *)p->maps[0].p, (uint8_t *)p->bmaps[0].p,
+                                                            (uint32_t *)p->fail.p, (RunResult *)p->res_dev.p);
+  p->launches++;
+  if (p->timing) CK(cudaEventRecord(p->ev[3], st));
+  k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->fail.p, nchunks, (RunResult *)p->res_dev.p);
+  p->launches++;
+  CK(cudaMemcpyAsync(p->res_host, p->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return KEX_OK;
+}
+
+// backward up-sweep over the first nchunks_eff chunk maps; returns the level count
+static int lam_up(kex_program *p, size_t nchunks_eff, size_t *cnt, int *nl, cudaStream_t st) {
+  const uint32_t NL = p->phases[p->sh_phase].fdev.NL;
+  level_counts(nchunks_eff, cnt, nl);
+  for (int l = 1; l < *nl; ++l) {
+    int rc = ensure(p, p->bmaps[l], cnt[l] * NL);
+    if (rc) return rc;
+    k_compose_rev<<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->bmaps[l - 1].p, cnt[l - 1], (uint8_t *)p->bmaps[l].p, NL);
+    p->launches++;
+  }
+  return KEX_OK;
+}
+
+static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t *d_out, size_t out_cap, size_t *out_len,
+                        cudaStream_t st) {
+  PhaseHost &ph = p->phases[p->sh_phase];
+  const PhaseDev &P = ph.dev;
+  const uint32_t NL = ph.fdev.NL;
+  *out_len = 0;
+  if (n_eff == 0) return KEX_OK;
+  if (lam_end >= NL || ((uintptr_t)d_out & 15u) != 0) return KEX_ERR_ARG;
+  const size_t ntiles = (n_eff + KEX_CHUNK - 1) / KEX_CHUNK;
+  if (ntiles >= 0xFFFFFFFFull) return KEX_ERR_UNSUPPORTED;
+  int rc;
+  size_t cnt[8];
+  int nl = 0;
+  level_counts(ntiles, cnt, &nl);
+  if (NL > 1) {
+    if ((rc = lam_up(p, ntiles, cnt, &nl, st))) return rc;
+    for (int l = 0; l < nl; ++l) if ((rc = ensure(p, p->lams[l], cnt[l]))) return rc;
+    k_set_u8<<<1, 1, 0, st>>>((uint8_t *)p->lams[nl - 1].p, lam_end);
+    p->launches++;
+    for (int l = nl - 1; l >= 1; --l) {
+      k_push_lam<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, st>>>((const uint8_t *)p->bmaps[l - 1].p, cnt[l - 1],
+                                                                  (const uint8_t *)p->lams[l].p, cnt[l],
+                                                                  (uint8_t *)p->lams[l - 1].p, NL);
+      p->launches++;
+    }
+  } else {
+    if ((rc = ensure(p, p->lams[0], 16))) return rc;
+  }
+  if ((rc = ensure(p, p->desc, ntiles * 8))) return rc;
+  if ((rc = ensure(p, p->ctl, sizeof(FastCtl)))) return rc;
+  CK(cudaMemsetAsync(p->desc.p, 0, ntiles * 8, st));
+  CK(cudaMemsetAsync(p->ctl.p, 0, sizeof(FastCtl), st));
+  const size_t smem = 2 * KEX_CHUNK + ph.stage_bytes + 32 + EF_RECCAP * 4 + 16 + ph.smem_ef_tables;
+  if (ph.ef_ctas_per_sm == 0 || ph.ef_stage_cfg != ph.stage_bytes) {
+    int occ = 0;
+    if (NL > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit_fast<true>, EF_NT, smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit_fast<false>, EF_NT, smem));
+    if (occ < 1) return KEX_ERR_UNSUPPORTED;
+    ph.ef_ctas_per_sm = occ;
+    ph.ef_stage_cfg = ph.stage_bytes;
+  }
+  const size_t resident = (size_t)ph.ef_ctas_per_sm * p->num_sms;
+  const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
+  if (p->timing) CK(cudaEventRecord(p->ev[4], st));
+  if (NL > 1)
+    k_emit_fast<true><<<grid, EF_NT, smem, st>>>(P, ph.fdev, p->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->samples.p,
+                                                 (const uint16_t *)p->starts[0].p, (const uint8_t *)p->lams[0].p,
+                                                 (unsigned long long *)p->desc.p, (FastCtl *)p->ctl.p, d_out, out_cap,
+                                                 ph.stage_bytes);
+  else
+    k_emit_fast<false><<<grid, EF_NT, smem, st>>>(P, ph.fdev, p->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->samples.p,
+                                                  (const uint16_t *)p->starts[0].p, (const uint8_t *)p->lams[0].p,
+                                                  (unsigned long long *)p->desc.p, (FastCtl *)p->ctl.p, d_out, out_cap,
+                                                  ph.stage_bytes);
+  p->launches++;
+  if (p->timing) CK(cudaEventRecord(p->ev[5], st));
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(p->ctl_host, p->ctl.p, sizeof(FastCtl), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (p->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
+  const size_t total = (size_t)p->ctl_host->total_out;
+  *out_len = total;
+  if (p->ctl_host->overflow || total > out_cap) return KEX_ERR_OUT_CAP;
+  // size the staging window for the next run from the observed out/in ratio
+  const double per_tile = (double)total / (double)ntiles;
+  uint32_t want = (uint32_t)(per_tile * 1.25) + 512;
+  want = (want + 1023u) & ~1023u;
+  if (want < 8192u) want = 8192u;
+  if (want > 49152u) want = 49152u;
+  if (want > ph.stage_bytes || want + 4096u < ph.stage_bytes) ph.stage_bytes = want;
+  return KEX_OK;
+}
+
 extern "C" int kex_shard_summarize(kex_program *p, const uint8_t *d_in, size_t n, uint16_t *h_state_map, void *stream) {
   if (!p || !h_state_map || (n && !d_in)) return KEX_ERR_ARG;
   if (p->phases.size() != 1) return KEX_ERR_UNSUPPORTED;
@@ -1051,16 +1311,24 @@ extern "C" int kex_shard_summarize(kex_program *p, const uint8_t *d_in, size_t n
   return KEX_OK;
 }
 
+extern "C" size_t kex_seam_bytes(const kex_program *p) {
+  if (!p || p->phases.empty()) return 0;
+  const PhaseHost &ph = p->phases[0];
+  return ph.fast ? ph.fdev.NL : ph.dev.R;
+}
+
 extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *end_state, size_t *fail_pos,
-                              uint8_t *h_fate_map, void *stream) {
-  if (!p || !end_state || !fail_pos || !h_fate_map) return KEX_ERR_ARG;
+                              uint8_t *h_seam, void *stream) {
+  if (!p || !end_state || !fail_pos || !h_seam) return KEX_ERR_ARG;
   CK(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const PhaseDev &P = p->phases[p->sh_phase].dev;
+  PhaseHost &ph = p->phases[p->sh_phase];
+  const PhaseDev &P = ph.dev;
   if (start_state > P.Q) return KEX_ERR_ARG;
+  const uint32_t nseam = ph.fast ? ph.fdev.NL : P.R;
   if (p->sh_n == 0) {
     *end_state = start_state; *fail_pos = (size_t)-1;
-    for (uint32_t r = 0; r < P.R; ++r) h_fate_map[r] = (uint8_t)r;
+    for (uint32_t r = 0; r < nseam; ++r) h_seam[r] = (uint8_t)r;
     return KEX_OK;
   }
   int rc = do_walk(p, start_state, st);
@@ -1069,7 +1337,43 @@ extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *en
   *fail_pos = (f == KEX_NONE64) ? (size_t)-1 : (size_t)f;
   *end_state = p->res_host->end_state;
   const size_t n_eff = (f == KEX_NONE64) ? p->sh_n : (size_t)f;
-  return do_fate_up(p, (n_eff + KEX_CHUNK - 1) / KEX_CHUNK, h_fate_map, st);
+  const size_t nchunks_eff = (n_eff + KEX_CHUNK - 1) / KEX_CHUNK;
+  if (!ph.fast) return do_fate_up(p, nchunks_eff, h_seam, st);
+  if (nseam == 1 || nchunks_eff == 0) {
+    for (uint32_t r = 0; r < nseam; ++r) h_seam[r] = (uint8_t)r;
+    return KEX_OK;
+  }
+  size_t cnt[8];
+  int nl = 0;
+  if ((rc = lam_up(p, nchunks_eff, cnt, &nl, st))) return rc;
+  CK(cudaMemcpyAsync(h_seam, p->bmaps[nl - 1].p, nseam, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return KEX_OK;
+}
+
+// Seam codes at the end of every shard from the shards' seam summaries (in
+// shard order) and the code of the end-of-input action.
+extern "C" int kex_stitch_live(const kex_program *p, const uint8_t *seams, size_t nshards, uint32_t final_code,
+                               uint32_t *codes) {
+  if (!p || !seams || !codes) return KEX_ERR_ARG;
+  const PhaseHost &ph = p->phases[0];
+  const size_t nb = ph.fast ? ph.fdev.NL : ph.dev.R;
+  uint32_t code = final_code;
+  for (size_t r = nshards; r-- > 0;) {
+    codes[r] = code;
+    const uint8_t *m = seams + r * nb;
+    if (ph.fast) {
+      if (code >= nb) return KEX_ERR_ARG;
+      code = m[code];
+    } else {
+      const uint32_t live = code | 1u;
+      uint32_t nx = 0;
+      for (uint32_t i = 1; i < nb; ++i)
+        if (m[i] != KEX_DEAD && ((live >> m[i]) & 1u)) nx |= 1u << i;
+      code = nx;
+    }
+  }
+  return KEX_OK;
 }
 
 extern "C" int kex_shard_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff, uint8_t *d_out, size_t out_cap,
@@ -1100,7 +1404,7 @@ static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t
   }
   const int32_t fa = failed ? -1 : ph.fin[end_state];
   const bool accept = fa >= 0;
-  const uint32_t live = accept ? ph.acts[fa].flush_mask : 0u;
+  const uint32_t live = accept ? final_code(ph, end_state) : 0u;
   size_t body = 0;
   int rc = do_emit(p, live, n_eff, d_out, out_cap, &body, st);
   if (rc == KEX_ERR_OUT_CAP) { *out_len = body + (accept ? ph.acts[fa].total_len : 0); return rc; }

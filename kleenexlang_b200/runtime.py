@@ -26,11 +26,11 @@ class KexError(RuntimeError):
 
 class KexInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
-        "nphases", "nstates", "nclasses", "nregs", "nactions", "max_out_per_byte", "chunk_bytes", "reserved")]
+        "nphases", "nstates", "nclasses", "nregs", "nactions", "max_out_per_byte", "chunk_bytes", "monoid_kernels")]
 
 
 EXPORTS = ["kex_load", "kex_free", "kex_info", "kex_run_device", "kex_run_host", "kex_shard_summarize",
-           "kex_shard_walk", "kex_shard_emit", "kex_final_action", "kex_out_bound", "kex_last_launch_count",
+           "kex_seam_bytes", "kex_shard_walk", "kex_stitch_live", "kex_shard_emit", "kex_final_action", "kex_out_bound", "kex_last_launch_count",
            "kex_set_timing", "kex_last_kernel_ms", "kex_strerror", "kex_last_cuda_error"]
 
 
@@ -57,6 +57,9 @@ def lib():
     L.kex_shard_summarize.argtypes = [vp, u8p, sz, ctypes.POINTER(ctypes.c_uint16), vp]
     L.kex_shard_walk.argtypes = [vp, u32, ctypes.POINTER(u32), ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_uint8), vp]
     L.kex_shard_emit.argtypes = [vp, u32, sz, u8p, sz, ctypes.POINTER(sz), vp]
+    L.kex_seam_bytes.argtypes = [vp]
+    L.kex_seam_bytes.restype = sz
+    L.kex_stitch_live.argtypes = [vp, ctypes.c_char_p, sz, u32, ctypes.POINTER(u32)]
     L.kex_final_action.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(u32),
                                    ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz)]
     L.kex_out_bound.argtypes = [vp, sz]
@@ -167,26 +170,38 @@ class CompiledProgram:
         self._check(self._L.kex_shard_summarize(self._h, d_in, n, m, stream))
         return list(m)
 
-    def shard_walk(self, start_state: int, stream: int = 0):
-        r = self.info()["nregs"]
-        end, fail = ctypes.c_uint32(), ctypes.c_size_t()
-        fate = (ctypes.c_uint8 * r)()
-        self._check(self._L.kex_shard_walk(self._h, start_state, ctypes.byref(end), ctypes.byref(fail), fate, stream))
-        fp = fail.value
-        return end.value, (None if fp == ctypes.c_size_t(-1).value else fp), list(fate)
+    def seam_bytes(self):
+        return self._L.kex_seam_bytes(self._h)
 
-    def shard_emit(self, live_end_mask: int, n_eff: int, d_out: int, out_cap: int, stream: int = 0):
+    def shard_walk(self, start_state: int, stream: int = 0):
+        """-> (end state, first failing position or None, seam summary bytes)."""
+        end, fail = ctypes.c_uint32(), ctypes.c_size_t()
+        seam = (ctypes.c_uint8 * self.seam_bytes())()
+        self._check(self._L.kex_shard_walk(self._h, start_state, ctypes.byref(end), ctypes.byref(fail), seam, stream))
+        fp = fail.value
+        return end.value, (None if fp == ctypes.c_size_t(-1).value else fp), bytes(seam)
+
+    def stitch_live(self, seams, final_code: int):
+        """Seam summaries of all shards (in order) + the code of the end-of-input
+        action -> seam code at the end of every shard."""
+        n = len(seams)
+        codes = (ctypes.c_uint32 * n)()
+        self._check(self._L.kex_stitch_live(self._h, b"".join(seams), n, final_code, codes))
+        return list(codes)
+
+    def shard_emit(self, seam_code: int, n_eff: int, d_out: int, out_cap: int, stream: int = 0):
         ol = ctypes.c_size_t()
-        rc = self._L.kex_shard_emit(self._h, live_end_mask, n_eff, d_out, out_cap, ctypes.byref(ol), stream)
+        rc = self._L.kex_shard_emit(self._h, seam_code, n_eff, d_out, out_cap, ctypes.byref(ol), stream)
         if rc == KEX_ERR_OUT_CAP:
             raise KexError(rc, "output buffer too small: need %d bytes" % ol.value)
         self._check(rc)
         return ol.value
 
     def final_action(self, state: int):
-        acc, mask = ctypes.c_int(), ctypes.c_uint32()
+        """-> (accepting, seam code of the end-of-input action, literal tail)."""
+        acc, code = ctypes.c_int(), ctypes.c_uint32()
         tail, tl = ctypes.c_void_p(), ctypes.c_size_t()
-        self._check(self._L.kex_final_action(self._h, state, ctypes.byref(acc), ctypes.byref(mask),
+        self._check(self._L.kex_final_action(self._h, state, ctypes.byref(acc), ctypes.byref(code),
                                              ctypes.byref(tail), ctypes.byref(tl)))
         data = ctypes.string_at(tail.value, tl.value) if tl.value else b""
-        return bool(acc.value), mask.value, data
+        return bool(acc.value), code.value, data

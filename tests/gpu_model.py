@@ -226,7 +226,7 @@ def run_fast_model(t, f, data: bytes, chunk: int = 64, sub: int = 8):
                 b = data[lo + ti * sub + j]
                 if typ == E_SYM:
                     out.append(b)
-                elif typ == E_CONST1:
+                elif typ == E_CONST1 and ln == 1:
                     out.append(x)
                 elif typ == E_TPL:
                     info, hmask = f.tplinfo[2 * x], f.tplinfo[2 * x + 1]

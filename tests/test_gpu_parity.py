@@ -21,11 +21,11 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 _cache = {}
 
 
-def gpu_prog(src, opt=3):
+def gpu_prog(src, opt=3, with_fast=True):
     from kleenexlang_b200.runtime import CompiledProgram
-    key = (src, opt)
+    key = (src, opt, with_fast)
     if key not in _cache:
-        _cache[key] = (CompiledProgram(compile_kex(src, opt)), build_ssts(src, opt))
+        _cache[key] = (CompiledProgram(compile_kex(src, opt, with_fast)), build_ssts(src, opt))
     return _cache[key]
 
 
@@ -72,6 +72,37 @@ def _check(prog, ssts, d):
 def test_synthetic_vs_oracle(name, opt):
     prog, ssts = gpu_prog(program_source(name), opt)
     d = workloads.GENERATORS[name](3 << 20, seed=21).tobytes()
+    _check(prog, ssts, d)
+
+
+@pytest.mark.parametrize("name", PROGS)
+def test_generic_kernels_vs_oracle(name):
+    """Blob without the monoid section: the generic kernels (any program up to
+    32 registers) must stay bit-exact too."""
+    prog, ssts = gpu_prog(program_source(name), 3, with_fast=False)
+    assert prog.info()["monoid_kernels"] == 0
+    d = workloads.GENERATORS[name](1 << 20, seed=22).tobytes()
+    _check(prog, ssts, d)
+    _check(prog, ssts, d[:300000] + b"\x01" + d[300001:])
+
+
+@pytest.mark.parametrize("name", PROGS)
+def test_monoid_kernels_selected(name):
+    prog, ssts = gpu_prog(program_source(name))
+    assert prog.info()["monoid_kernels"] == 1
+    # twice: the second run uses the staging window sized from the first
+    d = workloads.GENERATORS[name](5 << 20, seed=23).tobytes()
+    _check(prog, ssts, d)
+    _check(prog, ssts, d)
+
+
+def test_output_capacity_error():
+    from kleenexlang_b200.runtime import KexError
+    prog, ssts = gpu_prog(program_source("csv2json"))
+    d = workloads.gen_csv(200000, seed=5).tobytes()
+    with pytest.raises(KexError) as ei:
+        prog.run(d, out_cap=len(d))
+    assert ei.value.code == -3
     _check(prog, ssts, d)
 
 
@@ -131,9 +162,9 @@ def test_sharded_entry_points(name):
     starts = stitch_states(maps, build_ssts(program_source(name))[0].initial)
     walks = [p.shard_walk(s) for p, s in zip(progs, starts)]
     assert all(w[1] is None for w in walks)
-    acc, mask, tail = progs[-1].final_action(walks[-1][0])
+    acc, code, tail = progs[-1].final_action(walks[-1][0])
     assert acc
-    lives = stitch_live([w[2] for w in walks], mask)
+    lives = stitch_live(progs[0], [w[2] for w in walks], code)
     outs = []
     for p, b, live in zip(progs, bufs, lives):
         o = torch.empty(6 * b.numel() + 64, dtype=torch.uint8, device="cuda")
