@@ -52,6 +52,13 @@ struct FastCtl {                 // device control block of one emit launch
 #define EF_VALMASK ((1ull << 62) - 1)
 
 __device__ __forceinline__ uint32_t byte_at(uint32_t w, int k) { return (w >> (8 * k)) & 0xFFu; }
+// byte k of w via one PRMT
+__device__ __forceinline__ uint32_t byte_prmt(uint32_t w, int k) { return __byte_perm(w, 0u, 0x4440u | (uint32_t)k); }
+// replace byte k of acc by byte 2 of e
+__device__ __forceinline__ uint32_t put_byte2(uint32_t acc, uint32_t e, int k) {
+  const uint32_t sel = k == 0 ? 0x3216u : k == 1 ? 0x3260u : k == 2 ? 0x3610u : 0x6210u;
+  return __byte_perm(acc, e, sel);
+}
 __device__ __forceinline__ uint32_t word_of(const uint4 &v, int k) {
   return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
 }
@@ -224,35 +231,45 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-struct EmitSmem {                 // pointers into the CTA's dynamic shared memory
-  uint8_t *cls4;                  // [256]   4 * class
-  uint32_t *trans2;               // [(Q+1)*C]
-  uint32_t *BE;                   // [NL*A]
-  uint8_t *mulB, *compB, *applyB; // backward monoid
-  uint32_t *tplinfo;
-  uint8_t *pool;
-  uint8_t *in[2];                 // 2 x EF_TILE input ring (TMA destination)
-  uint8_t *stage;                 // staging window
-  uint32_t *recs;                 // [EF_RECCAP] template records
-  uint64_t *bar;                  // [2] mbarriers of the input ring
+// Dynamic shared memory of k_emit_fast.  Everything is addressed as an offset
+// from this symbol so that the compiler keeps the accesses in the shared
+// address space (LDS/STS with 32-bit addresses) instead of generic loads.
+extern __shared__ __align__(128) uint8_t smem_ef[];
+
+struct EmitSmem {                 // byte offsets into smem_ef
+  uint32_t cls4;                  // [256]   4 * class
+  uint32_t trans2;                // u32 [(Q+1)*C]
+  uint32_t BE;                    // u32 [NL*A]
+  uint32_t mulB, compB, applyB;   // backward monoid
+  uint32_t tplinfo;               // u32 [2*NT]
+  uint32_t pool;
+  uint32_t in[1];                 // EF_TILE input tile (TMA destination)
+  uint32_t stage;                 // staging window
+  uint32_t recs;                  // u32 [EF_RECCAP] template records
+  uint32_t bar;                   // u64 mbarrier of the input tile
 };
+#define SM8(off) (smem_ef[(off)])
+#define SM16(off) (*(uint16_t *)(smem_ef + (off)))
+#define SM32(off) (*(uint32_t *)(smem_ef + (off)))
 
 // forward walk of one thread's 32 bytes: action ids packed 4 per word, backward
 // monoid element of the sub-chunk
+// In shared memory the low 16 bits of a trans2 entry hold the byte offset of
+// the next state's row (so a step is LOP + IADD + LDS), bits 16-23 the action,
+// bits 24-31 twice the backward generator; mulB is u16 [NB][NG] holding the
+// byte offset of the product's row (so a step is LEA.HI + LDS).
 template <bool FULL, bool REGS>
-__device__ __forceinline__ void ef_forward(const EmitSmem &S, const uint32_t (&w)[8], uint32_t cnt_pos, uint32_t C4,
-                                           uint32_t NG, uint32_t &s, uint32_t (&ap)[8], uint32_t &mb) {
+__device__ __forceinline__ void ef_forward(const EmitSmem &S, const uint32_t (&w)[8], uint32_t cnt_pos,
+                                           uint32_t &srow, uint32_t (&ap)[8], uint32_t &mbrow) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
+    if ((j & 3) == 0) ap[j >> 2] = 0;
     if (FULL || (uint32_t)j < cnt_pos) {
-      const uint32_t b = byte_at(w[j >> 2], j & 3);
-      const uint32_t e = *(const uint32_t *)((const uint8_t *)S.trans2 + s * C4 + S.cls4[b]);
-      s = e & 0xFFFFu;
-      if ((j & 3) == 0) ap[j >> 2] = 0;
-      ap[j >> 2] |= ((e >> 16) & 0xFFu) << (8 * (j & 3));
-      if (REGS) mb = S.mulB[mb * NG + (e >> 24)];
-    } else if ((j & 3) == 0) {
-      ap[j >> 2] = 0;
+      const uint32_t b = byte_prmt(w[j >> 2], j & 3);
+      const uint32_t e = SM32(srow + SM8(b));          // cls4 lives at offset 0
+      srow = e & 0xFFFFu;
+      ap[j >> 2] = put_byte2(ap[j >> 2], e, j & 3);
+      if (REGS) mbrow = SM16(mbrow + (e >> 24));
     }
   }
 }
@@ -262,33 +279,34 @@ __device__ __forceinline__ void ef_forward(const EmitSmem &S, const uint32_t (&w
 // staging window and push template records.  MODE 2: write everything to
 // global memory byte by byte (tiles whose output exceeds the staging window).
 template <bool FULL, int MODE>
-__device__ __forceinline__ uint32_t ef_backward(const EmitSmem &S, const FastDev &F, const uint32_t (&w)[8],
-                                                const uint32_t (&ap)[8], uint32_t cnt_pos, uint32_t lamoff,
-                                                uint32_t o, uint32_t *recp, uint8_t *gout) {
+__device__ __forceinline__ uint32_t ef_backward(const EmitSmem &S, const uint32_t (&w)[8], const uint32_t (&ap)[8],
+                                                uint32_t cnt_pos, uint32_t lamoff, uint32_t o, uint32_t recp,
+                                                uint8_t *gout) {
   uint32_t acc = 0;
 #pragma unroll
   for (int j = 31; j >= 0; --j) {
     if (FULL || (uint32_t)j < cnt_pos) {
-      const uint32_t a = byte_at(ap[j >> 2], j & 3);
-      const uint32_t e = *(const uint32_t *)((const uint8_t *)S.BE + lamoff + a * 4u);
+      const uint32_t a = byte_prmt(ap[j >> 2], j & 3);
+      const uint32_t e = SM32(S.BE + lamoff + a * 4u);
       lamoff = e & 0xFFFCu;
       if (MODE == 0) {
         acc += e & 0x00FF0002u;
       } else {
         const uint32_t len = (e >> 16) & 0xFFu;
         o -= len;
-        const uint32_t b = byte_at(w[j >> 2], j & 3);
+        const uint32_t b = byte_prmt(w[j >> 2], j & 3);
         if (e & 2u) {
           if (MODE == 1) {
-            *recp++ = o | ((e >> 24) << 16) | (b << 24);
+            SM32(recp) = o | ((e >> 24) << 16) | (b << 24);
+            recp += 4u;
           } else {
-            const uint32_t i0 = S.tplinfo[2 * (e >> 24)], hm = S.tplinfo[2 * (e >> 24) + 1];
-            const uint8_t *tp = S.pool + (i0 & 0xFFFFu);
-            for (uint32_t k = 0; k < len; ++k) gout[o + k] = (k < 32u && ((hm >> k) & 1u)) ? (uint8_t)b : tp[k];
+            const uint32_t i0 = SM32(S.tplinfo + 8u * (e >> 24)), hm = SM32(S.tplinfo + 8u * (e >> 24) + 4u);
+            const uint32_t tp = S.pool + (i0 & 0xFFFFu);
+            for (uint32_t k = 0; k < len; ++k) gout[o + k] = (k < 32u && ((hm >> k) & 1u)) ? (uint8_t)b : SM8(tp + k);
           }
         } else if (len) {
           const uint8_t v = (uint8_t)((e & 1u) ? b : (e >> 24));
-          if (MODE == 1) S.stage[o] = v; else gout[o] = v;
+          if (MODE == 1) SM8(o) = v; else gout[o] = v;
         }
       }
     }
@@ -302,97 +320,94 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
             const uint16_t *__restrict__ samples, const uint16_t *__restrict__ chunk_start,
             const uint8_t *__restrict__ lam_end, unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl,
             uint8_t *__restrict__ out, size_t out_cap, uint32_t stage_bytes) {
-  extern __shared__ __align__(128) uint8_t smem_ef[];
-  uint8_t *smem = smem_ef;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t Q1 = P.Q + 1, C = P.C, A = P.A, NL = F.NL, NB = F.NB, NG = F.NG;
   const uint32_t C4 = 4u * C;
-  __shared__ uint32_t s_tile[2];
+  const uint32_t mb_recip = 65536u / (2u * NG) + 1u;
+  __shared__ uint32_t s_tile;
   __shared__ unsigned long long s_warp[EF_NT / 32];
   __shared__ unsigned long long s_total, s_gbase;
   __shared__ uint32_t s_wmb[EF_NT / 32];
 
-  // ---- carve shared memory: input ring first (TMA wants 16-byte alignment; we give 128)
+  // ---- carve shared memory: tables first (their offsets must fit 16 bits),
+  // then the input tile (TMA destination, 128-byte aligned) and the staging window
   EmitSmem S;
-  uint8_t *sp = smem;
-  S.in[0] = sp; sp += EF_TILE;
-  S.in[1] = sp; sp += EF_TILE;
-  S.stage = sp; sp += stage_bytes + 32u;
-  S.recs = (uint32_t *)sp; sp += EF_RECCAP * 4u;
-  S.bar = (uint64_t *)sp; sp += 16;
-  S.trans2 = (uint32_t *)sp; sp += Q1 * C * 4u;
-  S.BE = (uint32_t *)sp; sp += NL * A * 4u;
-  S.tplinfo = (uint32_t *)sp; sp += F.NT * 8u;
-  S.cls4 = sp; sp += 256;
-  S.mulB = sp; sp += NB * NG;
+  uint32_t sp = 0;
+  S.cls4 = sp; sp += 256;             // offset 0: the class lookup needs no address arithmetic
+  S.trans2 = sp; sp += Q1 * C * 4u;
+  S.BE = sp; sp += NL * A * 4u;
+  S.tplinfo = sp; sp += F.NT * 8u;
+  S.mulB = sp; sp += NB * NG * 2u;
   S.compB = sp; sp += NB * NB;
   S.applyB = sp; sp += NB * NL;
-  S.pool = sp;
-  for (uint32_t i = tid; i < Q1 * C; i += EF_NT) S.trans2[i] = F.trans2[i];
-  for (uint32_t i = tid; i < NL * A; i += EF_NT) S.BE[i] = F.BE[i];
-  for (uint32_t i = tid; i < 2u * F.NT; i += EF_NT) S.tplinfo[i] = F.tplinfo[i];
-  for (uint32_t i = tid; i < 256; i += EF_NT) S.cls4[i] = (uint8_t)(4u * P.cls[i]);
-  for (uint32_t i = tid; i < NB * NG; i += EF_NT) S.mulB[i] = F.mulB[i];
-  for (uint32_t i = tid; i < NB * NB; i += EF_NT) S.compB[i] = F.compB[i];
-  for (uint32_t i = tid; i < NB * NL; i += EF_NT) S.applyB[i] = F.applyB[i];
-  for (uint32_t i = tid; i < F.pool_len; i += EF_NT) S.pool[i] = F.pool[i];
-
-  auto tile_len = [&](uint32_t t) -> uint32_t {
-    const size_t base = (size_t)t * EF_TILE;
-    return (uint32_t)((n_eff - base < EF_TILE) ? (n_eff - base) : EF_TILE);
-  };
-  auto issue_load = [&](uint32_t t, uint32_t slot) {   // one thread
-    const uint32_t bytes = (tile_len(t) + 15u) & ~15u;
-    mbar_expect_tx(&S.bar[slot], bytes);
-    bulk_g2s(S.in[slot], in + (size_t)t * EF_TILE, bytes, &S.bar[slot]);
-  };
-
-  if (tid == 0) {
-    mbar_init(&S.bar[0], 1);
-    mbar_init(&S.bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t t0 = atomicAdd(&ctl->ticket, 1u);
-    s_tile[0] = t0;
-    if (t0 < ntiles) issue_load(t0, 0);
+  S.pool = sp; sp += F.pool_len;
+  sp = (sp + 127u) & ~127u;
+  S.in[0] = sp; sp += EF_TILE;
+  S.stage = sp; sp += stage_bytes + 32u;
+  S.recs = sp; sp += EF_RECCAP * 4u;
+  S.bar = sp;
+  for (uint32_t i = tid; i < Q1 * C; i += EF_NT) {
+    const uint32_t e = F.trans2[i];
+    SM32(S.trans2 + 4u * i) = (e & 0x00FF0000u) | ((e >> 24) << 25) | (S.trans2 + (e & 0xFFFFu) * C4);
   }
-  __syncthreads();
+  for (uint32_t i = tid; i < NL * A; i += EF_NT) SM32(S.BE + 4u * i) = F.BE[i];
+  for (uint32_t i = tid; i < 2u * F.NT; i += EF_NT) SM32(S.tplinfo + 4u * i) = F.tplinfo[i];
+  for (uint32_t i = tid; i < 256; i += EF_NT) SM8(S.cls4 + i) = (uint8_t)(4u * P.cls[i]);
+  for (uint32_t i = tid; i < NB * NG; i += EF_NT) SM16(S.mulB + 2u * i) = (uint16_t)(S.mulB + (uint32_t)F.mulB[i] * NG * 2u);
+  for (uint32_t i = tid; i < NB * NB; i += EF_NT) SM8(S.compB + i) = F.compB[i];
+  for (uint32_t i = tid; i < NB * NL; i += EF_NT) SM8(S.applyB + i) = F.applyB[i];
+  for (uint32_t i = tid; i < F.pool_len; i += EF_NT) SM8(S.pool + i) = F.pool[i];
+  uint64_t *bar = (uint64_t *)(smem_ef + S.bar);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   uint32_t it = 0;
   while (true) {
-    const uint32_t slot = it & 1u;
-    const uint32_t tile = s_tile[slot];
-    if (tile >= ntiles) break;
-    // the previous tile's bulk store must have finished reading the staging
-    // window before anybody writes to it again (waited for below, before the
-    // write pass); take the next ticket and prefetch its input now
+    // A tile is claimed only when its CTA starts working on it: every tile with
+    // a smaller ticket is then finished or in flight, so the chained scan
+    // below never waits for work that has not started.
+    __syncthreads();
     if (tid == 0) {
-      const uint32_t tn = atomicAdd(&ctl->ticket, 1u);
-      s_tile[slot ^ 1u] = tn;
-      if (tn < ntiles) issue_load(tn, slot ^ 1u);
+      const uint32_t t = atomicAdd(&ctl->ticket, 1u);
+      s_tile = t;
+      if (t < ntiles) {
+        const size_t base = (size_t)t * EF_TILE;
+        const uint32_t tl = (uint32_t)((n_eff - base < EF_TILE) ? (n_eff - base) : EF_TILE);
+        const uint32_t bytes = (tl + 15u) & ~15u;
+        mbar_expect_tx(&bar[0], bytes);
+        bulk_g2s(smem_ef + S.in[0], in + base, bytes, &bar[0]);
+      }
     }
-    const uint32_t tlen = tile_len(tile);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= ntiles) break;
+    const size_t tbase = (size_t)tile * EF_TILE;
+    const uint32_t tlen = (uint32_t)((n_eff - tbase < EF_TILE) ? (n_eff - tbase) : EF_TILE);
     const bool full = (tlen == EF_TILE);
     const uint32_t lo = tid * EF_SUB;
     const uint32_t cnt_pos = (lo < tlen) ? ((tlen - lo < EF_SUB) ? (tlen - lo) : EF_SUB) : 0u;
-    // start state of this thread's sub-chunk
+    // start state of this thread's sub-chunk (independent of the input bytes)
     uint32_t s = P.Q;
     if (cnt_pos) {
       const uint32_t smp = samples[(size_t)tile * EF_NT + tid];
       s = __ldg(F.applyF + (size_t)smp * Q1 + chunk_start[tile]);
     }
     const uint32_t lam_tile = REGS ? lam_end[tile] : 0u;
-    mbar_wait(&S.bar[slot], (it >> 1) & 1u);
+    mbar_wait(&bar[0], it & 1u);
     uint32_t w[8];
     {
-      const uint4 v0 = *(const uint4 *)(S.in[slot] + lo), v1 = *(const uint4 *)(S.in[slot] + lo + 16);
+      const uint4 v0 = *(const uint4 *)(smem_ef + S.in[0] + lo), v1 = *(const uint4 *)(smem_ef + S.in[0] + lo + 16);
       w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
       w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
     }
     // ---- forward walk
     uint32_t ap[8];
-    uint32_t mb = 0;
-    if (full) ef_forward<true, REGS>(S, w, cnt_pos, C4, NG, s, ap, mb);
-    else ef_forward<false, REGS>(S, w, cnt_pos, C4, NG, s, ap, mb);
+    uint32_t srow = S.trans2 + s * C4, mbrow = S.mulB;
+    if (full) ef_forward<true, REGS>(S, w, cnt_pos, srow, ap, mbrow);
+    else ef_forward<false, REGS>(S, w, cnt_pos, srow, ap, mbrow);
+    const uint32_t mb = ((mbrow - S.mulB) * mb_recip) >> 16;      // row offset -> element id (exact, NB <= 255)
 
     // ---- live set at the end of this thread's sub-chunk
     uint32_t lamoff = 0;
@@ -402,19 +417,19 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t y = __shfl_down_sync(0xFFFFFFFFu, x, d);
-        if (lane + d < 32u) x = S.compB[x * NB + y];
+        if (lane + d < 32u) x = SM8(S.compB + x * NB + y);
       }
       uint32_t ex = __shfl_down_sync(0xFFFFFFFFu, x, 1);     // elements of the later lanes
       if (lane == 31u) ex = 0;
       if (lane == 0) s_wmb[warp] = x;
       __syncthreads();
-      for (uint32_t w2 = warp + 1; w2 < EF_NT / 32; ++w2) ex = S.compB[ex * NB + s_wmb[w2]];
-      lamoff = (uint32_t)S.applyB[ex * NL + lam_tile] * A * 4u;
+      for (uint32_t w2 = warp + 1; w2 < EF_NT / 32; ++w2) ex = SM8(S.compB + ex * NB + s_wmb[w2]);
+      lamoff = (uint32_t)SM8(S.applyB + ex * NL + lam_tile) * A * 4u;
     }
 
     // ---- count
-    const uint32_t acc = full ? ef_backward<true, 0>(S, F, w, ap, cnt_pos, lamoff, 0, nullptr, nullptr)
-                              : ef_backward<false, 0>(S, F, w, ap, cnt_pos, lamoff, 0, nullptr, nullptr);
+    const uint32_t acc = full ? ef_backward<true, 0>(S, w, ap, cnt_pos, lamoff, 0, 0, nullptr)
+                              : ef_backward<false, 0>(S, w, ap, cnt_pos, lamoff, 0, 0, nullptr);
     const uint32_t cnt = acc >> 16, nrec = (acc & 0xFFFFu) >> 1;
     unsigned long long v = (unsigned long long)cnt | ((unsigned long long)nrec << 32);
     unsigned long long xs = v;
@@ -425,33 +440,24 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
     }
     if (lane == 31u) s_warp[warp] = xs;
     __syncthreads();
-    if (tid == 0) {
-      unsigned long long t = 0;
-      for (uint32_t k = 0; k < EF_NT / 32; ++k) { const unsigned long long q = s_warp[k]; s_warp[k] = t; t += q; }
-      s_total = t;
-    }
-    __syncthreads();
-    const unsigned long long incl = s_warp[warp] + xs;
-    const uint32_t o_end = (uint32_t)incl;                       // bytes up to and including this thread
-    const uint32_t rec_base = (uint32_t)((incl - v) >> 32);
-    const uint32_t total = (uint32_t)s_total, total_recs = (uint32_t)(s_total >> 32);
-
-    // ---- chained scan of the tile totals (decoupled look-back), warp 0
     if (warp == 0) {
+      // ---- tile total, then the chained scan of the tile totals (decoupled look-back)
+      unsigned long long t = 0;
+      for (uint32_t k = 0; k < EF_NT / 32; ++k) t += s_warp[k];
+      const uint32_t total = (uint32_t)t;
       if (lane == 0) st_desc(desc + tile, EF_FLAG_AGG | (unsigned long long)total);
       unsigned long long excl = 0;
       long long idx = (long long)tile - 1;
       bool ok = true;
-      while (idx >= 0 && ok) {
+      while (idx >= 0) {
         const long long j = idx - lane;
         unsigned long long d = EF_FLAG_INC;
         if (j >= 0) {
           uint32_t spins = 0;
-          do {
-            d = ld_desc(desc + j);
-            if ((d >> 62) == 0 && ++spins > (1u << 24)) break;
-            if ((d >> 62) == 0) __nanosleep(32);
-          } while ((d >> 62) == 0);
+          while (((d = ld_desc(desc + j)) >> 62) == 0) {
+            if (++spins > (1u << 22)) break;
+            __nanosleep(20);
+          }
         }
         if (__any_sync(0xFFFFFFFFu, (d >> 62) == 0)) { ok = false; break; }
         const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
@@ -467,11 +473,18 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
         if (!ok) atomicExch(&ctl->error, 1u);
         st_desc(desc + tile, EF_FLAG_INC | (excl + total));
         s_gbase = excl;
+        s_total = t;
         if (tile == ntiles - 1) ctl->total_out = excl + total;
-        if (it) bulk_wait_read0();      // staging window free again
+        bulk_wait_read0();              // the previous tile's bulk store has read the staging window
       }
     }
     __syncthreads();
+    unsigned long long wbase = 0;
+    for (uint32_t k = 0; k < warp; ++k) wbase += s_warp[k];
+    const unsigned long long incl = wbase + xs;
+    const uint32_t o_end = (uint32_t)incl;                       // bytes up to and including this thread
+    const uint32_t rec_base = (uint32_t)((incl - v) >> 32);
+    const uint32_t total = (uint32_t)s_total, total_recs = (uint32_t)(s_total >> 32);
     const unsigned long long gbase = s_gbase;
     const uint32_t shift = (uint32_t)(gbase & 15ull);
     const bool fits = gbase + total <= (unsigned long long)out_cap;
@@ -479,47 +492,46 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
       if (tid == 0) atomicExch(&ctl->overflow, 1u);
     } else if (total + shift <= stage_bytes && total_recs <= EF_RECCAP) {
       // ---- write pass into the staging window
-      uint32_t *recp = S.recs + rec_base;
-      if (full) ef_backward<true, 1>(S, F, w, ap, cnt_pos, lamoff, shift + o_end, recp, nullptr);
-      else ef_backward<false, 1>(S, F, w, ap, cnt_pos, lamoff, shift + o_end, recp, nullptr);
+      const uint32_t recp = S.recs + 4u * rec_base;
+      if (full) ef_backward<true, 1>(S, w, ap, cnt_pos, lamoff, S.stage + shift + o_end, recp, nullptr);
+      else ef_backward<false, 1>(S, w, ap, cnt_pos, lamoff, S.stage + shift + o_end, recp, nullptr);
       __syncthreads();
       // ---- templates: one lane per record
       for (uint32_t r = tid; r < total_recs; r += EF_NT) {
-        const uint32_t rc = S.recs[r];
+        const uint32_t rc = SM32(S.recs + 4u * r);
         const uint32_t o = rc & 0xFFFFu, id = (rc >> 16) & 0xFFu, b = rc >> 24;
-        const uint32_t i0 = S.tplinfo[2 * id], hm = S.tplinfo[2 * id + 1];
-        const uint8_t *tp = S.pool + (i0 & 0xFFFFu);
+        const uint32_t i0 = SM32(S.tplinfo + 8u * id), hm = SM32(S.tplinfo + 8u * id + 4u);
+        const uint32_t tp = S.pool + (i0 & 0xFFFFu);
         const uint32_t len = i0 >> 16;
-        uint8_t *dst = S.stage + o;
-        for (uint32_t k = 0; k < len; ++k) dst[k] = (k < 32u && ((hm >> k) & 1u)) ? (uint8_t)b : tp[k];
+        for (uint32_t k = 0; k < len; ++k) SM8(o + k) = (k < 32u && ((hm >> k) & 1u)) ? (uint8_t)b : SM8(tp + k);
       }
       fence_async_smem();
       __syncthreads();
       // ---- staging window -> global: 16-byte words aligned to the destination
       uint8_t *gal = out + (gbase - shift);
+      const uint8_t *stg = smem_ef + S.stage;
       const uint32_t end = shift + total;
       const uint32_t w_lo = shift ? 1u : 0u;
       const uint32_t w_hi = end >> 4;
       if (tid == 0 && w_hi > w_lo) {
-        bulk_s2g(gal + 16u * w_lo, S.stage + 16u * w_lo, 16u * (w_hi - w_lo));
+        bulk_s2g(gal + 16u * w_lo, stg + 16u * w_lo, 16u * (w_hi - w_lo));
         bulk_commit();
       }
       if (shift) {
         const uint32_t he = (end < 16u) ? end : 16u;
-        for (uint32_t b2 = shift + tid; b2 < he; b2 += EF_NT) gal[b2] = S.stage[b2];
+        for (uint32_t b2 = shift + tid; b2 < he; b2 += EF_NT) gal[b2] = stg[b2];
       }
       if (w_hi >= w_lo) {
         for (uint32_t b2 = (w_hi << 4) + tid; b2 < end; b2 += EF_NT)
-          if (b2 >= shift) gal[b2] = S.stage[b2];
+          if (b2 >= shift) gal[b2] = stg[b2];
       }
     } else {
       // ---- output of this tile exceeds the staging window: direct byte stores
       uint8_t *g = out + gbase;
-      if (full) ef_backward<true, 2>(S, F, w, ap, cnt_pos, lamoff, o_end, nullptr, g);
-      else ef_backward<false, 2>(S, F, w, ap, cnt_pos, lamoff, o_end, nullptr, g);
+      if (full) ef_backward<true, 2>(S, w, ap, cnt_pos, lamoff, o_end, 0, g);
+      else ef_backward<false, 2>(S, w, ap, cnt_pos, lamoff, o_end, 0, g);
     }
     ++it;
-    __syncthreads();
   }
   if (tid == 0) bulk_wait_read0();
 }

@@ -736,10 +736,12 @@ static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph
   ph.lam_masks.assign((const uint32_t *)(f + off[11]), (const uint32_t *)(f + off[11]) + NL);
 
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  const size_t tables = al(4ull * Q1 * C) + al(4ull * NL * A) + al(8ull * NT) + 256 + al((size_t)NB * NG) +
-                        al((size_t)NB * NB) + al((size_t)NB * NL) + al(pool_len);
+  // shared-memory layout of k_emit_fast: tables, then tile, staging window, records
+  size_t tables = 4ull * Q1 * C + 4ull * NL * A + 8ull * NT + 2ull * NB * NG + 256 + (size_t)NB * NB + (size_t)NB * NL + pool_len;
+  tables = (tables + 127) & ~(size_t)127;
   ph.smem_fm = 256 + al(2ull * NM * C);
-  if (tables > 40 * 1024 || ph.smem_fm > 160 * 1024) return KEX_OK;      // generic kernels
+  // limits of the kernels' packed fields; beyond them the generic kernels run the phase
+  if (tables > 24 * 1024 || ph.smem_fm > 160 * 1024 || NG > 127 || (size_t)Q1 * C * 4 > 65535) return KEX_OK;
   const uint8_t *db = (const uint8_t *)ph.d_blob + fo;                  // the blob is already on the device
   FastDev &d = ph.fdev;
   d.NM = NM; d.NL = NL; d.NG = NG; d.NB = NB; d.NT = NT; d.pool_len = pool_len; d.max_emit = max_emit;
@@ -1251,7 +1253,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
   if ((rc = ensure(p, p->ctl, sizeof(FastCtl)))) return rc;
   CK(cudaMemsetAsync(p->desc.p, 0, ntiles * 8, st));
   CK(cudaMemsetAsync(p->ctl.p, 0, sizeof(FastCtl), st));
-  const size_t smem = 2 * KEX_CHUNK + ph.stage_bytes + 32 + EF_RECCAP * 4 + 16 + ph.smem_ef_tables;
+  const size_t smem = ph.smem_ef_tables + KEX_CHUNK + ph.stage_bytes + 32 + EF_RECCAP * 4 + 16;
   if (ph.ef_ctas_per_sm == 0 || ph.ef_stage_cfg != ph.stage_bytes) {
     int occ = 0;
     if (NL > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit_fast<true>, EF_NT, smem));
@@ -1287,7 +1289,8 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
   uint32_t want = (uint32_t)(per_tile * 1.25) + 512;
   want = (want + 1023u) & ~1023u;
   if (want < 8192u) want = 8192u;
-  if (want > 49152u) want = 49152u;
+  const uint32_t stage_max = (uint32_t)((65535 - 64 - KEX_CHUNK - ph.smem_ef_tables) & ~(size_t)1023);   // record offsets are 16 bits
+  if (want > stage_max) want = stage_max;
   if (want > ph.stage_bytes || want + 4096u < ph.stage_bytes) ph.stage_bytes = want;
   return KEX_OK;
 }
