@@ -275,9 +275,10 @@ __device__ __forceinline__ void ef_forward(const EmitSmem &S, const uint32_t (&w
 }
 
 // backward walk: bytes emitted per position.  MODE 0: count (returns bytes in
-// bits 16.., 2*records in the low bits).  MODE 1: write single bytes to the
-// staging window and push template records.  MODE 2: write everything to
-// global memory byte by byte (tiles whose output exceeds the staging window).
+// bits 16.., 2*records in the low bits).  MODE 1: write the copied input bytes
+// to the staging window and push one record per template (branch-free: every
+// store is predicated).  MODE 2: write everything to global memory byte by
+// byte (tiles whose output exceeds the staging window).
 template <bool FULL, int MODE>
 __device__ __forceinline__ uint32_t ef_backward(const EmitSmem &S, const uint32_t (&w)[8], const uint32_t (&ap)[8],
                                                 uint32_t cnt_pos, uint32_t lamoff, uint32_t o, uint32_t recp,
@@ -291,22 +292,24 @@ __device__ __forceinline__ uint32_t ef_backward(const EmitSmem &S, const uint32_
       lamoff = e & 0xFFFCu;
       if (MODE == 0) {
         acc += e & 0x00FF0002u;
+      } else if (MODE == 1) {
+        o -= byte_prmt(e, 2);
+        // record: staging offset | template id << 16 | input byte << 24
+        const uint32_t t = __byte_perm(o, e, 0x3710u);
+        const uint32_t sel = (j & 3) == 0 ? 0x4210u : (j & 3) == 1 ? 0x5210u : (j & 3) == 2 ? 0x6210u : 0x7210u;
+        const uint32_t rec = __byte_perm(t, w[j >> 2], sel);
+        if (e & 2u) { SM32(recp) = rec; recp += 4u; }
+        if (e & 1u) SM8(o) = (uint8_t)(rec >> 24);
       } else {
         const uint32_t len = (e >> 16) & 0xFFu;
         o -= len;
         const uint32_t b = byte_prmt(w[j >> 2], j & 3);
         if (e & 2u) {
-          if (MODE == 1) {
-            SM32(recp) = o | ((e >> 24) << 16) | (b << 24);
-            recp += 4u;
-          } else {
-            const uint32_t i0 = SM32(S.tplinfo + 8u * (e >> 24)), hm = SM32(S.tplinfo + 8u * (e >> 24) + 4u);
-            const uint32_t tp = S.pool + (i0 & 0xFFFFu);
-            for (uint32_t k = 0; k < len; ++k) gout[o + k] = (k < 32u && ((hm >> k) & 1u)) ? (uint8_t)b : SM8(tp + k);
-          }
-        } else if (len) {
-          const uint8_t v = (uint8_t)((e & 1u) ? b : (e >> 24));
-          if (MODE == 1) SM8(o) = v; else gout[o] = v;
+          const uint32_t i0 = SM32(S.tplinfo + 8u * (e >> 24)), hm = SM32(S.tplinfo + 8u * (e >> 24) + 4u);
+          const uint32_t tp = S.pool + (i0 & 0xFFFFu);
+          for (uint32_t k = 0; k < len; ++k) gout[o + k] = (k < 32u && ((hm >> k) & 1u)) ? (uint8_t)b : SM8(tp + k);
+        } else if (e & 1u) {
+          gout[o] = (uint8_t)b;
         }
       }
     }
@@ -314,8 +317,32 @@ __device__ __forceinline__ uint32_t ef_backward(const EmitSmem &S, const uint32_
   return acc;
 }
 
+// One record: copy template `id` to staging offset o.  The pool is stored four
+// times, copy v shifted left by v bytes, so that an unaligned 32-bit read at
+// byte x is the aligned word at (x & ~3) of copy (x & 3): the middle of a
+// template moves as whole words, at most 3 + 3 edge bytes move one by one.
+__device__ __forceinline__ void ef_copy_template(const EmitSmem &S, uint32_t pool_stride, uint32_t rc) {
+  const uint32_t o = rc & 0xFFFFu, id = (rc >> 16) & 0xFFu;
+  const uint32_t i0 = SM32(S.tplinfo + 8u * id), hm = SM32(S.tplinfo + 8u * id + 4u);
+  const uint32_t src = i0 & 0xFFFFu, len = i0 >> 16;
+  uint32_t head = (4u - (o & 3u)) & 3u;
+  if (head > len) head = len;
+  uint32_t k = 0;
+  for (; k < head; ++k) SM8(o + k) = SM8(S.pool + src + k);
+  const uint32_t x = src + k;                                  // pool byte offset of the first whole word
+  const uint32_t wsrc = S.pool + (x & 3u) * pool_stride + (x & ~3u);
+  const uint32_t nw = (len - k) >> 2;
+  for (uint32_t i = 0; i < nw; ++i) SM32(o + k + 4u * i) = SM32(wsrc + 4u * i);
+  k += 4u * nw;
+  for (; k < len; ++k) SM8(o + k) = SM8(S.pool + src + k);
+  if (hm) {
+    const uint8_t b = (uint8_t)(rc >> 24);
+    for (uint32_t h = hm; h; h &= h - 1u) SM8(o + (uint32_t)__ffs((int)h) - 1u) = b;
+  }
+}
+
 template <bool REGS>
-__global__ void __launch_bounds__(EF_NT, 6)
+__global__ void __launch_bounds__(EF_NT, 8)
 k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
             const uint16_t *__restrict__ samples, const uint16_t *__restrict__ chunk_start,
             const uint8_t *__restrict__ lam_end, unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl,
@@ -340,7 +367,9 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
   S.mulB = sp; sp += NB * NG * 2u;
   S.compB = sp; sp += NB * NB;
   S.applyB = sp; sp += NB * NL;
-  S.pool = sp; sp += F.pool_len;
+  sp = (sp + 3u) & ~3u;
+  const uint32_t pool_stride = (F.pool_len + 7u) & ~3u;     // four shifted copies, each padded by a word
+  S.pool = sp; sp += 4u * pool_stride;
   sp = (sp + 127u) & ~127u;
   S.in[0] = sp; sp += EF_TILE;
   S.stage = sp; sp += stage_bytes + 32u;
@@ -356,7 +385,10 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
   for (uint32_t i = tid; i < NB * NG; i += EF_NT) SM16(S.mulB + 2u * i) = (uint16_t)(S.mulB + (uint32_t)F.mulB[i] * NG * 2u);
   for (uint32_t i = tid; i < NB * NB; i += EF_NT) SM8(S.compB + i) = F.compB[i];
   for (uint32_t i = tid; i < NB * NL; i += EF_NT) SM8(S.applyB + i) = F.applyB[i];
-  for (uint32_t i = tid; i < F.pool_len; i += EF_NT) SM8(S.pool + i) = F.pool[i];
+  for (uint32_t i = tid; i < 4u * pool_stride; i += EF_NT) {
+    const uint32_t v = i / pool_stride, k = i - v * pool_stride + v;       // copy v, byte k of the pool
+    SM8(S.pool + i) = (k < F.pool_len) ? F.pool[k] : (uint8_t)0;
+  }
   uint64_t *bar = (uint64_t *)(smem_ef + S.bar);
   if (tid == 0) {
     mbar_init(&bar[0], 1);
@@ -497,14 +529,7 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
       else ef_backward<false, 1>(S, w, ap, cnt_pos, lamoff, S.stage + shift + o_end, recp, nullptr);
       __syncthreads();
       // ---- templates: one lane per record
-      for (uint32_t r = tid; r < total_recs; r += EF_NT) {
-        const uint32_t rc = SM32(S.recs + 4u * r);
-        const uint32_t o = rc & 0xFFFFu, id = (rc >> 16) & 0xFFu, b = rc >> 24;
-        const uint32_t i0 = SM32(S.tplinfo + 8u * id), hm = SM32(S.tplinfo + 8u * id + 4u);
-        const uint32_t tp = S.pool + (i0 & 0xFFFFu);
-        const uint32_t len = i0 >> 16;
-        for (uint32_t k = 0; k < len; ++k) SM8(o + k) = (k < 32u && ((hm >> k) & 1u)) ? (uint8_t)b : SM8(tp + k);
-      }
+      for (uint32_t r = tid; r < total_recs; r += EF_NT) ef_copy_template(S, pool_stride, SM32(S.recs + 4u * r));
       fence_async_smem();
       __syncthreads();
       // ---- staging window -> global: 16-byte words aligned to the destination

@@ -737,7 +737,8 @@ static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph
 
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
   // shared-memory layout of k_emit_fast: tables, then tile, staging window, records
-  size_t tables = 4ull * Q1 * C + 4ull * NL * A + 8ull * NT + 2ull * NB * NG + 256 + (size_t)NB * NB + (size_t)NB * NL + pool_len;
+  size_t tables = 4ull * Q1 * C + 4ull * NL * A + 8ull * NT + 2ull * NB * NG + 256 + (size_t)NB * NB + (size_t)NB * NL + 4 +
+                  4ull * ((pool_len + 7) & ~3u);
   tables = (tables + 127) & ~(size_t)127;
   ph.smem_fm = 256 + al(2ull * NM * C);
   // limits of the kernels' packed fields; beyond them the generic kernels run the phase

@@ -122,7 +122,7 @@ def run_model(t, data: bytes, chunk: int = 7):
 # blob (kleenexlang_b200/fasttab.py), same pass structure as
 # kleenexlang_b200/csrc/kex_fast.cuh.
 def run_fast_model(t, f, data: bytes, chunk: int = 64, sub: int = 8):
-    from kleenexlang_b200.fasttab import E_NONE, E_SYM, E_CONST1, E_TPL
+    from kleenexlang_b200.fasttab import E_SYM, E_TPL
     Q, C, A = t.Q, t.C, t.A
     FAIL = Q
     n = len(data)
@@ -226,8 +226,6 @@ def run_fast_model(t, f, data: bytes, chunk: int = 64, sub: int = 8):
                 b = data[lo + ti * sub + j]
                 if typ == E_SYM:
                     out.append(b)
-                elif typ == E_CONST1 and ln == 1:
-                    out.append(x)
                 elif typ == E_TPL:
                     info, hmask = f.tplinfo[2 * x], f.tplinfo[2 * x + 1]
                     off, tl = info & 0xFFFF, (info >> 16) & 0xFF
