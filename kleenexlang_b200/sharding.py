@@ -26,3 +26,15 @@ def stitch_live(prog, seams, final_code):
     seam code of the end-of-input action (0 when the run rejects).
     -> seam code at the end of every shard."""
     return prog.stitch_live(list(seams), final_code)
+
+
+def stitch_codes(seams, final_code):
+    """Pure-Python statement of `kex_stitch_live` for monoid-kernel programs:
+    seams[r][code] = live-set index at the start of shard r given the index at
+    its end."""
+    codes = [0] * len(seams)
+    code = final_code
+    for r in range(len(seams) - 1, -1, -1):
+        codes[r] = code
+        code = seams[r][code]
+    return codes

@@ -165,6 +165,8 @@ def test_sharded_entry_points(name):
     acc, code, tail = progs[-1].final_action(walks[-1][0])
     assert acc
     lives = stitch_live(progs[0], [w[2] for w in walks], code)
+    from kleenexlang_b200.sharding import stitch_codes
+    assert lives == stitch_codes([list(w[2]) for w in walks], code)
     outs = []
     for p, b, live in zip(progs, bufs, lives):
         o = torch.empty(6 * b.numel() + 64, dtype=torch.uint8, device="cuda")
