@@ -1,0 +1,674 @@
+// kex_v3.cuh -- warp-autonomous monoid kernels ("v3").
+//
+// Same algorithm as kex_fast.cuh (forward transition monoid, live-set monoid,
+// the tile that creates a byte writes it), re-laid for the B200 SM:
+//
+//   k3_fwd     state chain of `matchN` (src/KMC/Program/Backends/C.hs:72-83)
+//              for all start states at once.  One thread walks two 4 KiB
+//              chunks interleaved (two independent dependent-load chains), two
+//              input bytes per table lookup (pair table: row offset of the
+//              product element), prefix element sampled every 16 bytes.
+//   k3_seams   per 1 KiB tile from its true start state: backward (live-set)
+//              element until it is a constant map; exact position of a failing
+//              transition (C.hs:79-81) by atomicMin.
+//   k3_emit    outputconst/outputarray/output and the register buffers of
+//              crt/crt.c:161-283.  One WARP per 1 KiB tile, no CTA barriers:
+//              each lane owns 32 input bytes as two independent 16-byte halves
+//              (ILP 2 in every pass).  Transition and emission tables are
+//              replicated once per lane in shared memory (entry stride 128 B:
+//              lane l only ever touches bank l, so the per-byte lookups are
+//              bank-conflict free) and hold absolute shared addresses, so a
+//              step is LEA.HI + LDS.  Passes per byte: forward (action id,
+//              backward element), count (IDP.4A accumulates length and record
+//              count at once), write (input bytes to a per-warp staging window,
+//              one record per template), then templates are copied word-wise
+//              and the window leaves with one TMA bulk store.  Tile totals are
+//              chained with a decoupled look-back, one descriptor per tile.
+#pragma once
+
+#define V3_TILE 1024u
+#define V3_SUB 16u
+#define V3_SPC (KEX_CHUNK / V3_SUB)     // samples per 4 KiB chunk (256)
+#define V3_SPT (V3_TILE / V3_SUB)       // samples per tile (64)
+#define V3_TPC (KEX_CHUNK / V3_TILE)    // tiles per chunk (4)
+#define V3_RECCAP 192u                  // template records per tile kept in shared memory
+#define V3_SMEM_MAX (227 * 1024)        // dynamic shared memory per CTA on sm_100
+
+struct V3Dev {
+  uint32_t ok;                 // phase runs on the v3 kernels
+  uint32_t log;                // log2 of the table entry stride in bytes: 7 = one copy per lane, 5 = one per 8 lanes
+  uint32_t o_mulB, o_trans, o_BE, o_cls, o_compB, o_applyB, o_tpl2, o_pool, o_slots, o_warp;   // byte offsets in dynamic smem
+  uint32_t pool_stride;
+  uint32_t NE;                 // NL * A emission entries
+  const uint32_t *be3;         // [NE]  len | T << 15 | S << 16 | (lam_before * A) << 24;  S: emits exactly the input byte
+  const uint32_t *tpl2;        // [NE]  pool offset | length << 16 | (hole offset + 1) << 24   (entries with T)
+  // forward pass
+  uint32_t pair;               // 1: fwdtab is the pair table [NM][C*C], 0: [NM][C]
+  uint32_t rowbytes;           // bytes per row of fwdtab
+  uint32_t recip;              // row offset -> element id: __umulhi(off, recip)
+  uint32_t fwd_entries;
+  const uint16_t *fwdtab;      // row byte offset of the product element
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t a) {       // data written by this kernel
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8_v(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+// acc - (byte 0 of e): unsigned bytes of e times signed bytes (-1, 0, 0, 0)
+__device__ __forceinline__ uint32_t sub_byte0(uint32_t e, uint32_t acc) {
+  int r;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(e), "r"(0x000000FF), "r"((int)acc));
+  return (uint32_t)r;
+}
+__device__ __forceinline__ void ld_stream32(const uint8_t *p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+
+// ------------------------------------------------------------------ k3_fwd
+// Shared memory: clsA[256] (u8, first byte of a pair: class * C * 2; single
+// steps: class * 2), clsB[256] (second byte: class * 2), then the table.
+#define F3_PAIR(m, w, k)                                                                          \
+  m = *(const uint16_t *)(tab + m + clsA[byte_at(w, k)] + clsB[byte_at(w, (k) + 1)]);
+#define F3_ONE(m, w, k) m = *(const uint16_t *)(tab + m + clsA[byte_at(w, k)]);
+#define F3_WORD(m, w)                                                                             \
+  if (PAIR) { F3_PAIR(m, w, 0) F3_PAIR(m, w, 2) } else { F3_ONE(m, w, 0) F3_ONE(m, w, 1) F3_ONE(m, w, 2) F3_ONE(m, w, 3) }
+#define F3_16(m, v) F3_WORD(m, v.x) F3_WORD(m, v.y) F3_WORD(m, v.z) F3_WORD(m, v.w)
+
+template <bool PAIR>
+__device__ __forceinline__ void f3_finish(const PhaseDev &P, const FastDev &F, const V3Dev &V, uint32_t m,
+                                          uint16_t *__restrict__ row) {
+  const uint32_t Q1 = P.Q + 1;
+  const uint32_t id = __umulhi(m, V.recip);
+  const uint16_t *ap = F.applyF + (size_t)id * Q1;
+  for (uint32_t q = 0; q < Q1; ++q) row[q] = ap[q];
+}
+
+// one chunk of arbitrary length (the last one); rolled
+template <bool PAIR>
+__device__ void f3_chunk_tail(const PhaseDev &P, const FastDev &F, const V3Dev &V, const uint8_t *clsA,
+                              const uint8_t *clsB, const uint8_t *tab, const uint8_t *__restrict__ p, uint32_t len,
+                              uint16_t *__restrict__ srow, uint16_t *__restrict__ mrow) {
+  uint32_t m = 0;
+  const uint32_t C = P.C;
+  for (uint32_t j = 0; j < len;) {
+    if ((j & (V3_SUB - 1u)) == 0) srow[j / V3_SUB] = (uint16_t)__umulhi(m, V.recip);
+    if (PAIR) {
+      if (j + 1 < len) {
+        m = *(const uint16_t *)(tab + m + clsA[p[j]] + clsB[p[j + 1]]);
+        j += 2;
+      } else {
+        // odd tail: one single step through the element table in global memory
+        const uint32_t id = __umulhi(m, V.recip);
+        m = (uint32_t)F.mulF[id * C + P.cls[p[j]]] * V.rowbytes;
+        j += 1;
+      }
+    } else {
+      m = *(const uint16_t *)(tab + m + clsA[p[j]]);
+      j += 1;
+    }
+  }
+  f3_finish<PAIR>(P, F, V, m, mrow);
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(512, 2)
+k3_fwd(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n, size_t nchunks,
+       uint16_t *__restrict__ samples, uint16_t *__restrict__ maps) {
+  extern __shared__ __align__(16) uint8_t smem_f3[];
+  uint8_t *clsA = smem_f3, *clsB = smem_f3 + 256;
+  uint8_t *tab = smem_f3 + 512;
+  const uint32_t C = P.C, Q1 = P.Q + 1;
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+    const uint32_t c = P.cls[i];
+    clsA[i] = (uint8_t)(PAIR ? c * C * 2u : c * 2u);
+    clsB[i] = (uint8_t)(c * 2u);
+  }
+  for (uint32_t i = threadIdx.x; i < V.fwd_entries; i += blockDim.x) ((uint16_t *)tab)[i] = V.fwdtab[i];
+  __syncthreads();
+  const size_t npairs = (nchunks + 1) / 2;
+  const uint32_t recip = V.recip;
+  for (size_t pr = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs; pr += (size_t)gridDim.x * blockDim.x) {
+    const size_t c0 = 2 * pr, c1 = c0 + 1;
+    const size_t base0 = c0 * KEX_CHUNK;
+    const bool two = c1 < nchunks;
+    const uint32_t len0 = (uint32_t)((n - base0 < KEX_CHUNK) ? (n - base0) : KEX_CHUNK);
+    const uint32_t len1 = two ? (uint32_t)((n - base0 - KEX_CHUNK < KEX_CHUNK) ? (n - base0 - KEX_CHUNK) : KEX_CHUNK) : 0u;
+    if (len0 == KEX_CHUNK && len1 == KEX_CHUNK) {
+      // two independent chains; the next 32 bytes of each are in flight while the
+      // current ones are walked (one full 32-byte sector per load)
+      const uint8_t *pa = in + base0, *pb = pa + KEX_CHUNK;
+      uint16_t *sa = samples + c0 * V3_SPC, *sb = sa + V3_SPC;
+      uint32_t ma = 0, mb = 0;
+      uint32_t ca[8], cb[8], na[8], nb[8];
+      ld_stream32(pa, ca);
+      ld_stream32(pb, cb);
+      uint32_t pend_a = 0, pend_b = 0;
+#pragma unroll 2
+      for (uint32_t blk = 0; blk < KEX_CHUNK / 32u; ++blk) {
+        const uint32_t nx = (blk + 1u < KEX_CHUNK / 32u) ? (blk + 1u) * 32u : blk * 32u;
+        ld_stream32(pa + nx, na);
+        ld_stream32(pb + nx, nb);
+        uint32_t ia0 = ma, ib0 = mb;
+        F3_WORD(ma, ca[0]) F3_WORD(mb, cb[0]) F3_WORD(ma, ca[1]) F3_WORD(mb, cb[1])
+        F3_WORD(ma, ca[2]) F3_WORD(mb, cb[2]) F3_WORD(ma, ca[3]) F3_WORD(mb, cb[3])
+        uint32_t ia1 = ma, ib1 = mb;
+        F3_WORD(ma, ca[4]) F3_WORD(mb, cb[4]) F3_WORD(ma, ca[5]) F3_WORD(mb, cb[5])
+        F3_WORD(ma, ca[6]) F3_WORD(mb, cb[6]) F3_WORD(ma, ca[7]) F3_WORD(mb, cb[7])
+        const uint32_t qa = __umulhi(ia0, recip) | (__umulhi(ia1, recip) << 16);
+        const uint32_t qb = __umulhi(ib0, recip) | (__umulhi(ib1, recip) << 16);
+        if (blk & 1u) {
+          *(uint2 *)(sa + (blk - 1u) * 2u) = make_uint2(pend_a, qa);
+          *(uint2 *)(sb + (blk - 1u) * 2u) = make_uint2(pend_b, qb);
+        } else {
+          pend_a = qa;
+          pend_b = qb;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ca[k] = na[k]; cb[k] = nb[k]; }
+      }
+      f3_finish<PAIR>(P, F, V, ma, maps + c0 * Q1);
+      f3_finish<PAIR>(P, F, V, mb, maps + c1 * Q1);
+    } else {
+      f3_chunk_tail<PAIR>(P, F, V, clsA, clsB, tab, in + base0, len0, samples + c0 * V3_SPC, maps + c0 * Q1);
+      if (two) f3_chunk_tail<PAIR>(P, F, V, clsA, clsB, tab, in + base0 + KEX_CHUNK, len1, samples + c1 * V3_SPC,
+                                   maps + c1 * Q1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k3_seams
+// One thread per 1 KiB tile.  Shared memory: cls[256], trans2 u32 [(Q+1)*C],
+// mulB u8 [NB*NG], constB [NB].
+__global__ void __launch_bounds__(256)
+k3_seams(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n, size_t ntiles,
+         const uint16_t *__restrict__ samples, const uint16_t *__restrict__ chunk_start,
+         const uint16_t *__restrict__ maps, uint8_t *__restrict__ bmaps, RunResult *__restrict__ res) {
+  extern __shared__ __align__(16) uint8_t smem_s3[];
+  const uint32_t Q = P.Q, Q1 = Q + 1, C = P.C, NL = F.NL, NG = F.NG, NB = F.NB;
+  uint8_t *cls = smem_s3;
+  uint32_t *tr = (uint32_t *)(smem_s3 + 256);
+  uint8_t *mulB = smem_s3 + 256 + 4u * Q1 * C;
+  uint8_t *constB = mulB + NB * NG;
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cls[i] = P.cls[i];
+  for (uint32_t i = threadIdx.x; i < Q1 * C; i += blockDim.x) tr[i] = F.trans2[i];
+  for (uint32_t i = threadIdx.x; i < NB * NG; i += blockDim.x) mulB[i] = F.mulB[i];
+  for (uint32_t i = threadIdx.x; i < NB; i += blockDim.x) constB[i] = F.constB[i];
+  __syncthreads();
+  const size_t tile = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= ntiles) return;
+  const size_t chunk = tile / V3_TPC;
+  const uint32_t cs = chunk_start[chunk];
+  uint32_t s = Q, endst = Q;
+  if (cs != Q) {
+    s = F.applyF[(size_t)samples[tile * V3_SPT] * Q1 + cs];
+    const bool last_in_chunk = ((tile + 1) % V3_TPC == 0) || (tile + 1 == ntiles);
+    endst = last_in_chunk ? maps[chunk * Q1 + cs] : F.applyF[(size_t)samples[(tile + 1) * V3_SPT] * Q1 + cs];
+  }
+  if (tile == ntiles - 1) res->end_state = endst;
+  const bool failing = (s != Q) && (endst == Q);
+  uint32_t mb = 0;
+  if (s != Q && (failing || NL > 1)) {
+    const size_t base = tile * V3_TILE;
+    const uint32_t len = (uint32_t)((n - base < V3_TILE) ? (n - base) : V3_TILE);
+    const uint8_t *p = in + base;
+    bool done = false;
+    for (uint32_t g = 0; g < len && !done; g += 16) {
+      const uint4 v = *(const uint4 *)(p + g);
+      const uint32_t lim = (len - g < 16u) ? (len - g) : 16u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (!done && (uint32_t)k < lim) {
+          const uint32_t e = tr[s * C + cls[byte_at(word_of(v, k >> 2), k & 3)]];
+          const uint32_t ns = e & 0xFFFFu;
+          if (ns == Q) {
+            atomicMin(&res->fail_pos, (unsigned long long)(base + g + k));
+            done = true;
+          } else {
+            s = ns;
+            mb = mulB[mb * NG + (e >> 24)];
+            if (!failing && constB[mb]) done = true;
+          }
+        }
+      }
+    }
+  }
+  if (NL > 1)
+    for (uint32_t l = 0; l < NL; ++l) bmaps[tile * NL + l] = __ldg(F.applyB + mb * NL + l);
+}
+
+// ------------------------------------------------------------------ k3_emit
+extern __shared__ __align__(1024) uint8_t smem_v3[];
+
+// put byte 0 of e into byte k of acc
+__device__ __forceinline__ uint32_t put_byte0(uint32_t acc, uint32_t e, int k) {
+  const uint32_t sel = k == 0 ? 0x3214u : k == 1 ? 0x3240u : k == 2 ? 0x3410u : 0x4210u;
+  return __byte_perm(acc, e, sel);
+}
+
+// Forward step.  E: last transition entry (bits 16-31: absolute shared address
+// of the current state's row in this lane's copy; byte 0: action; byte 1:
+// 2 * backward generator).  MB: absolute address of the backward element's row
+// (256-byte rows of u16 row addresses).
+template <int LOG, bool REGS>
+__device__ __forceinline__ void v3_fstep(uint32_t cls_abs, uint32_t &E, uint32_t &MB, uint32_t w, uint32_t &ap, int k) {
+  // the class table is 256-byte aligned: one PRMT extracts the byte and adds the table address
+  const uint32_t c = lds_u8(__byte_perm(w, cls_abs, 0x7650u | (uint32_t)k));
+  E = lds_u32((E >> 16) + (c << LOG));
+  ap = put_byte0(ap, E, k);
+  if (REGS) MB = lds_u16(__byte_perm(MB, E, 0x3215u));
+}
+
+template <int LOG, bool REGS, bool FULL>
+__device__ __forceinline__ void v3_forward(uint32_t cls_abs, const uint32_t (&w)[8], uint32_t cnt_pos, uint32_t &EA,
+                                           uint32_t &EB, uint32_t &MA, uint32_t &MB, uint32_t (&ap)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ap[k] = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (FULL || (uint32_t)j < cnt_pos) v3_fstep<LOG, REGS>(cls_abs, EA, MA, w[j >> 2], ap[j >> 2], j & 3);
+    if (FULL || (uint32_t)(j + 16) < cnt_pos) v3_fstep<LOG, REGS>(cls_abs, EB, MB, w[4 + (j >> 2)], ap[4 + (j >> 2)], j & 3);
+  }
+}
+
+// Emission entry address of action a under the live set encoded in EL (byte 3
+// = lam * A; bits 24-LOG .. 23 are zero, so EL >> (24-LOG) = (lam * A) << LOG).
+template <int LOG>
+__device__ __forceinline__ uint32_t v3_be_addr(uint32_t pbe, uint32_t EL, uint32_t apw, int k) {
+  const uint32_t a = byte_prmt(apw, k);
+  return (pbe + (a << LOG)) + (EL >> (24 - LOG));
+}
+
+// count pass over both halves: byte length in the low 14 bits, records above
+template <int LOG>
+__device__ __forceinline__ void v3_count(uint32_t pbe, const uint32_t (&ap)[8], uint32_t &ELA, uint32_t &ELB,
+                                         uint32_t &accA, uint32_t &accB) {
+#pragma unroll
+  for (int j = 15; j >= 0; --j) {
+    ELA = lds_u32(v3_be_addr<LOG>(pbe, ELA, ap[j >> 2], j & 3));
+    accA = __dp4a(ELA, 0x00008001u, accA);
+    ELB = lds_u32(v3_be_addr<LOG>(pbe, ELB, ap[4 + (j >> 2)], j & 3));
+    accB = __dp4a(ELB, 0x00008001u, accB);
+  }
+}
+
+template <int LOG>
+__device__ __forceinline__ void v3_wstep(uint32_t pbe, uint32_t &EL, uint32_t apw, uint32_t w, int k, uint32_t &o,
+                                         uint32_t &recp) {
+  const uint32_t addr = v3_be_addr<LOG>(pbe, EL, apw, k);
+  EL = lds_u32(addr);
+  o = sub_byte0(EL, o);
+  const uint32_t b = k == 0 ? w : byte_prmt(w, k);
+  if (EL & 0x10000u) sts_u8(o, b);
+  if (EL & 0x8000u) {
+    // staging address (18 bits) | entry address / 4 << 18; the input byte, for a template with a hole
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(recp), "r"(o + (addr << 16)), "r"(b) : "memory");
+    recp += 8u;
+  }
+}
+
+template <int LOG>
+__device__ __forceinline__ void v3_write(uint32_t pbe, const uint32_t (&ap)[8], const uint32_t (&w)[8], uint32_t ELA,
+                                         uint32_t ELB, uint32_t oA, uint32_t oB, uint32_t recpA, uint32_t recpB) {
+#pragma unroll
+  for (int j = 15; j >= 0; --j) {
+    v3_wstep<LOG>(pbe, ELA, ap[j >> 2], w[j >> 2], j & 3, oA, recpA);
+    v3_wstep<LOG>(pbe, ELB, ap[4 + (j >> 2)], w[4 + (j >> 2)], j & 3, oB, recpB);
+  }
+}
+
+// One template record: the literal bytes go to the staging window word-wise
+// (the pool is stored four times, copy v shifted by v bytes, so the unaligned
+// source of an aligned destination word is one aligned load).
+__device__ __forceinline__ void v3_copy_template(uint32_t pool_abs, uint32_t pool_stride, uint32_t o, uint32_t t,
+                                                 uint32_t byte) {
+  const uint32_t src = t & 0xFFFFu, len = (t >> 16) & 0xFFu;
+  // head bytes up to the first aligned destination word, whole words, tail bytes:
+  // straight-line and predicated, so the lanes of a warp do not diverge
+  uint32_t head = (4u - (o & 3u)) & 3u;
+  if (head > len) head = len;
+  const uint32_t nw = (len - head) >> 2, tail = (len - head) & 3u;
+  const uint32_t ps = pool_abs + src;
+#pragma unroll
+  for (uint32_t k = 0; k < 3; ++k)
+    if (k < head) sts_u8(o + k, lds_u8(ps + k));
+  const uint32_t x = src + head;                       // pool offset of the first whole word
+  const uint32_t wsrc = pool_abs + (x & 3u) * pool_stride + (x & ~3u);
+  const uint32_t wdst = o + head;
+#pragma unroll
+  for (uint32_t i = 0; i < 6; ++i)
+    if (i < nw) sts_u32(wdst + 4u * i, lds_u32(wsrc + 4u * i));
+  for (uint32_t i = 6; i < nw; ++i) sts_u32(wdst + 4u * i, lds_u32(wsrc + 4u * i));
+  const uint32_t tb = head + 4u * nw;
+#pragma unroll
+  for (uint32_t k = 0; k < 3; ++k)
+    if (k < tail) sts_u8(o + tb + k, lds_u8(ps + tb + k));
+  if (t >> 24) sts_u8(o + (t >> 24) - 1u, byte);       // the hole takes the input byte
+}
+
+template <int LOG, bool REGS>
+__global__ void __launch_bounds__(1024, 1)
+k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
+        const uint16_t *__restrict__ samples, const uint16_t *__restrict__ chunk_start,
+        const uint8_t *__restrict__ lam_end, unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl,
+        uint8_t *__restrict__ out, size_t out_cap, uint32_t stage_bytes, uint32_t warp_bytes) {
+  constexpr uint32_t STRIDE = 1u << LOG, REP = STRIDE / 4u;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const uint32_t Q = P.Q, Q1 = Q + 1, C = P.C, A = P.A, NL = F.NL, NB = F.NB, NG = F.NG;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_v3);
+  const uint32_t slot4 = (lane & (REP - 1u)) * 4u;
+
+  // ---- tables (once per CTA)
+  const uint32_t mulB_abs = base + V.o_mulB, trans_abs = base + V.o_trans, be_abs = base + V.o_BE;
+  if ((mulB_abs & 255u) || ((base + V.o_cls) & 255u) || be_abs + V.NE * STRIDE > 65536u) __trap();
+  for (uint32_t i = tid; i < NB * NG; i += blockDim.x) {
+    const uint32_t r = i / NG, g = i - r * NG;
+    *(uint16_t *)(smem_v3 + V.o_mulB + r * 256u + 2u * g) = (uint16_t)(mulB_abs + (uint32_t)F.mulB[i] * 256u);
+  }
+  for (uint32_t i = tid; i < Q1 * C * REP; i += blockDim.x) {
+    const uint32_t ent = i / REP, s = i - ent * REP;
+    const uint32_t e = F.trans2[ent];
+    const uint32_t row = trans_abs + (e & 0xFFFFu) * C * STRIDE + s * 4u;
+    *(uint32_t *)(smem_v3 + V.o_trans + ent * STRIDE + s * 4u) = (row << 16) | ((e >> 16) & 0xFFu) | ((e >> 24) << 9);
+  }
+  for (uint32_t i = tid; i < V.NE * REP; i += blockDim.x) {
+    const uint32_t ent = i / REP, s = i - ent * REP;
+    *(uint32_t *)(smem_v3 + V.o_BE + ent * STRIDE + s * 4u) = V.be3[ent];
+  }
+  for (uint32_t i = tid; i < 256; i += blockDim.x) smem_v3[V.o_cls + i] = P.cls[i];
+  for (uint32_t i = tid; i < NB * NB; i += blockDim.x) smem_v3[V.o_compB + i] = F.compB[i];
+  for (uint32_t i = tid; i < NB * NL; i += blockDim.x) smem_v3[V.o_applyB + i] = F.applyB[i];
+  for (uint32_t i = tid; i < V.NE; i += blockDim.x) *(uint32_t *)(smem_v3 + V.o_tpl2 + 4u * i) = V.tpl2[i];
+  for (uint32_t i = tid; i < 4u * V.pool_stride; i += blockDim.x) {
+    const uint32_t v = i / V.pool_stride, k = i - v * V.pool_stride + v;
+    smem_v3[V.o_pool + i] = (k < F.pool_len) ? F.pool[k] : (uint8_t)0;
+  }
+  __syncthreads();
+
+  const uint32_t cls_abs = base + V.o_cls, pool_abs = base + V.o_pool, tpl2_abs = base + V.o_tpl2;
+  const uint32_t pbe = be_abs + slot4;
+  const uint32_t wreg = V.o_warp + warp * warp_bytes;            // this warp's staging window, then its records
+  const uint32_t stage_abs = base + wreg;
+  const uint32_t recs_abs = stage_abs + stage_bytes + 32u;
+  const uint8_t *compB = smem_v3 + V.o_compB, *applyB = smem_v3 + V.o_applyB;
+  // A group is the nwork consecutive tiles the worker warps of one CTA process
+  // at a time.  The last warp of the CTA is the scan warp: it collects the tile
+  // totals of the group from shared memory, chains ONE descriptor per group with
+  // a decoupled look-back, and hands every worker its global output offset.  The
+  // workers do not wait for it until their staging window is complete, so the
+  // look-back latency hides behind the write pass.
+  //   named barrier 1: workers arrive (totals published), scan warp waits
+  //   named barrier 2: scan warp arrives (offsets published), workers wait
+  const uint32_t nwork = nwarp - 1u;
+  volatile uint32_t *slots = (volatile uint32_t *)(smem_v3 + V.o_slots);                             // [2][32] tile totals
+  volatile unsigned long long *bases = (volatile unsigned long long *)(smem_v3 + V.o_slots + 256u);  // [2][32] output offsets
+  const uint32_t ngroups = (ntiles + nwork - 1u) / nwork;
+  const uint32_t bar_n = blockDim.x;
+  uint32_t par = 0;
+
+  if (warp == nwork) {
+    // =============================================================== scan warp
+    for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x, par ^= 1u) {
+      asm volatile("bar.sync 1, %0;" ::"r"(bar_n) : "memory");
+      const uint32_t tv = (lane < nwork) ? slots[par * 32u + lane] : 0u;
+      uint32_t inc_s = tv;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc_s, d);
+        if (lane >= (uint32_t)d) inc_s += y;
+      }
+      const uint32_t gsum = __shfl_sync(0xFFFFFFFFu, inc_s, 31);
+      if (lane == 0) st_desc(desc + grp, EF_FLAG_AGG | (unsigned long long)gsum);
+      // every lane polls 8 descriptors (a window of 256 groups: all groups in flight
+      // are covered by one round trip to L2), nearest first
+      unsigned long long gex = 0;
+      long long idx = (long long)grp - 1;
+      bool ok = true;
+      while (idx >= 0 && ok) {
+        unsigned long long d[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const long long j = idx - (long long)(lane + 32u * k);
+          d[k] = (j >= 0) ? ld_desc(desc + j) : EF_FLAG_INC;
+        }
+        bool hit = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (!hit) {
+            const long long j = idx - (long long)(lane + 32u * k);
+            uint32_t spins = 0;
+            while ((d[k] >> 62) == 0) {
+              if (++spins > (1u << 22)) break;
+              __nanosleep(20);
+              d[k] = ld_desc(desc + j);
+            }
+            if (__any_sync(0xFFFFFFFFu, (d[k] >> 62) == 0)) { ok = false; hit = true; }
+            const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (d[k] >> 62) == 2);
+            const uint32_t first = inc ? (uint32_t)(__ffs((int)inc) - 1) : 31u;
+            unsigned long long c = (lane <= first) ? (d[k] & EF_VALMASK) : 0ull;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o2);
+            gex += c;
+            if (inc) hit = true;
+          }
+        }
+        if (hit) break;
+        idx -= 256;
+      }
+      if (lane == 0) {
+        if (!ok) atomicExch(&ctl->error, 1u);
+        st_desc(desc + grp, EF_FLAG_INC | (gex + gsum));
+        if (grp == ngroups - 1) ctl->total_out = gex + gsum;
+      }
+      bases[par * 32u + lane] = gex + (unsigned long long)(inc_s - tv);
+      __threadfence_block();
+      asm volatile("bar.arrive 2, %0;" ::"r"(bar_n) : "memory");
+    }
+    return;
+  }
+
+  // ================================================================= workers
+  for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x, par ^= 1u) {
+    const uint32_t tile = grp * nwork + warp;
+    const bool active = tile < ntiles;
+    const size_t tbase = (size_t)tile * V3_TILE;
+    const uint32_t tlen = active ? (uint32_t)((n_eff - tbase < V3_TILE) ? (n_eff - tbase) : V3_TILE) : 0u;
+    const bool full = (tlen == V3_TILE);
+    const uint32_t lo = lane * 32u;
+    const uint32_t cnt_pos = (lo < tlen) ? ((tlen - lo < 32u) ? (tlen - lo) : 32u) : 0u;
+    uint32_t w[8];
+    if (full) {
+      ld_stream32(in + tbase + lo, w);
+    } else {
+      // 16-byte pieces that start inside the tile (the input buffer is 16-byte granular)
+      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+      if (lo < tlen) v0 = *(const uint4 *)(in + tbase + lo);
+      if (lo + 16u < tlen) v1 = *(const uint4 *)(in + tbase + lo + 16u);
+      w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+      w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+    }
+    // start states of the two halves
+    uint32_t sA = Q, sB = Q;
+    if (cnt_pos) {
+      const uint32_t cs = chunk_start[tile / V3_TPC];
+      const uint32_t smp = *(const uint32_t *)(samples + (size_t)tile * V3_SPT + 2u * lane);
+      sA = __ldg(F.applyF + (size_t)(smp & 0xFFFFu) * Q1 + cs);
+      if (cnt_pos > 16u) sB = __ldg(F.applyF + (size_t)(smp >> 16) * Q1 + cs);
+    }
+    const uint32_t lam_tile = (REGS && active) ? lam_end[tile] : 0u;
+
+    // ---- forward walk
+    uint32_t ap[8];
+    uint32_t EA = (trans_abs + sA * C * STRIDE + slot4) << 16, EB = (trans_abs + sB * C * STRIDE + slot4) << 16;
+    uint32_t MA = mulB_abs, MB = mulB_abs;
+    if (full) v3_forward<LOG, REGS, true>(cls_abs, w, cnt_pos, EA, EB, MA, MB, ap);
+    else v3_forward<LOG, REGS, false>(cls_abs, w, cnt_pos, EA, EB, MA, MB, ap);
+
+    // ---- live set after each half
+    uint32_t lamT = 0, lamH = 0;                     // after the thread's last byte / after half A
+    if (REGS) {
+      const uint32_t mbA = (MA - mulB_abs) >> 8, mbB = (MB - mulB_abs) >> 8;
+      uint32_t x = compB[mbA * NB + mbB];            // this thread's element; suffix composition inside the warp
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_down_sync(0xFFFFFFFFu, x, d);
+        if (lane + d < 32u) x = compB[x * NB + y];
+      }
+      uint32_t ex = __shfl_down_sync(0xFFFFFFFFu, x, 1);
+      if (lane == 31u) ex = 0;
+      lamT = applyB[ex * NL + lam_tile];
+      lamH = applyB[mbB * NL + lamT];
+    }
+
+    // ---- count
+    uint32_t ELA = (lamH * A) << 24, ELB = (lamT * A) << 24;
+    uint32_t accA = 0, accB = 0;
+    {
+      uint32_t ea = ELA, eb = ELB;
+      v3_count<LOG>(pbe, ap, ea, eb, accA, accB);
+    }
+    const uint32_t cntA = accA & 0x3FFFu, cntB = accB & 0x3FFFu, nrA = accA >> 14, nrB = accB >> 14;
+    const uint32_t v = (cntA + cntB) | ((nrA + nrB) << 20);
+    uint32_t xs = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xs, d);
+      if (lane >= (uint32_t)d) xs += y;
+    }
+    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, xs, 31);
+    const uint32_t total = tot & 0xFFFFFu, total_recs = tot >> 20;
+
+    // ---- publish the tile total to the scan warp; prefetch this warp's next tile
+    if (lane == 0) slots[par * 32u + warp] = total;
+    {
+      const size_t nt = (size_t)tile + (size_t)gridDim.x * nwork;
+      if (nt < ntiles) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(in + nt * V3_TILE + lane * 32u));
+        if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(samples + nt * V3_SPT + lane * 16u));
+      }
+    }
+    __threadfence_block();
+    asm volatile("bar.arrive 1, %0;" ::"r"(bar_n) : "memory");
+    const uint32_t o_end = xs & 0xFFFFFu;                        // bytes up to and including this thread
+    const uint32_t rec_excl = (xs >> 20) - (nrA + nrB);
+    if (total + 16u <= stage_bytes && total_recs <= V3_RECCAP) {
+      // ---- write pass: input bytes into the staging window (tile-relative, so it
+      // does not need the global offset), one record per template
+      const uint32_t oB = stage_abs + o_end, oA = oB - cntB;
+      const uint32_t recpA = recs_abs + 8u * rec_excl, recpB = recpA + 8u * nrA;
+      v3_write<LOG>(pbe, ap, w, ELA, ELB, oA, oB, recpA, recpB);
+      __syncwarp();
+      // ---- templates: one lane per record
+      for (uint32_t r = lane; r < total_recs; r += 32u) {
+        const uint32_t rc = lds_u32_v(recs_abs + 8u * r), rb = lds_u32_v(recs_abs + 8u * r + 4u);
+        const uint32_t ent = (((rc >> 18) << 2) - be_abs) >> LOG;
+        v3_copy_template(pool_abs, V.pool_stride, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
+      }
+      __syncwarp();
+      // ---- global offset of this tile, then staging window -> global with
+      // 16-byte stores aligned to the destination: destination chunk c holds
+      // output bytes [16c - a, 16c - a + 16), a = offset mod 16
+      asm volatile("bar.sync 2, %0;" ::"r"(bar_n) : "memory");
+      const unsigned long long gbase = bases[par * 32u + warp];
+      if (gbase + total > (unsigned long long)out_cap) {
+        if (lane == 0) atomicExch(&ctl->overflow, 1u);
+      } else {
+        const uint32_t a = (uint32_t)(gbase & 15ull);
+        uint8_t *gal = out + (gbase - a);
+        const uint32_t end = a + total;                             // in destination-chunk coordinates
+        const uint32_t c_lo = a ? 1u : 0u, c_hi = end >> 4;         // whole chunks [c_lo, c_hi)
+        const uint32_t m = (16u - a) & 15u, rw = m >> 2, sh = (m & 3u) * 8u;
+        for (uint32_t c = c_lo + lane; c < c_hi; c += 32u) {
+          // source bytes start at 16c - a = 16(c - c_lo) + m  (relative to the window)
+          const uint32_t sa = stage_abs + 16u * (c - c_lo);
+          uint32_t W[8];
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(W[0]), "=r"(W[1]), "=r"(W[2]), "=r"(W[3]) : "r"(sa) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(W[4]), "=r"(W[5]), "=r"(W[6]), "=r"(W[7]) : "r"(sa + 16u) : "memory");
+          uint4 r4;
+          if (rw == 0) {
+            r4 = make_uint4(__funnelshift_r(W[0], W[1], sh), __funnelshift_r(W[1], W[2], sh),
+                            __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh));
+          } else if (rw == 1) {
+            r4 = make_uint4(__funnelshift_r(W[1], W[2], sh), __funnelshift_r(W[2], W[3], sh),
+                            __funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh));
+          } else if (rw == 2) {
+            r4 = make_uint4(__funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh),
+                            __funnelshift_r(W[4], W[5], sh), __funnelshift_r(W[5], W[6], sh));
+          } else {
+            r4 = make_uint4(__funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh),
+                            __funnelshift_r(W[5], W[6], sh), __funnelshift_r(W[6], W[7], sh));
+          }
+          *(uint4 *)(gal + 16u * c) = r4;
+        }
+        // head (destination bytes a..15 of chunk 0) and tail (after the last whole chunk)
+        const uint8_t *stg = smem_v3 + wreg;
+        if (a) {
+          const uint32_t he = (end < 16u) ? end : 16u;
+          for (uint32_t b2 = a + lane; b2 < he; b2 += 32u) gal[b2] = stg[b2 - a];
+        }
+        if (c_hi >= c_lo) {
+          for (uint32_t b2 = (c_hi << 4) + lane; b2 < end; b2 += 32u)
+            if (b2 >= a) gal[b2] = stg[b2 - a];
+        }
+      }
+      __syncwarp();
+    } else {
+      // ---- the tile's output exceeds the staging window: byte stores to global.
+      // Input words and action ids are parked in the (idle) staging window so
+      // that the loop can stay rolled.
+      asm volatile("bar.sync 2, %0;" ::"r"(bar_n) : "memory");
+      const unsigned long long gbase = bases[par * 32u + warp];
+      if (gbase + total > (unsigned long long)out_cap) {
+        if (lane == 0) atomicExch(&ctl->overflow, 1u);
+        continue;
+      }
+      const uint32_t sp = stage_abs + lane * 64u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sts_u32(sp + 4u * k, w[k]); sts_u32(sp + 32u + 4u * k, ap[k]); }
+      __syncwarp();
+      uint8_t *g = out + gbase;
+      uint32_t o = o_end, EL = ELB;
+      for (int j = 31; j >= 0; --j) {
+        const uint32_t a = lds_u8_v(sp + 32u + (uint32_t)j), b = lds_u8_v(sp + (uint32_t)j);
+        const uint32_t addr = (pbe + (a << LOG)) + (EL >> (24 - LOG));
+        EL = lds_u32(addr);
+        o -= EL & 0xFFu;
+        if (EL & 0x10000u) g[o] = (uint8_t)b;
+        if (EL & 0x8000u) {
+          const uint32_t t = lds_u32(tpl2_abs + 4u * ((addr - slot4 - be_abs) >> LOG));
+          const uint32_t src = t & 0xFFFFu, tl = (t >> 16) & 0xFFu, hole = t >> 24;
+          for (uint32_t k = 0; k < tl; ++k) g[o + k] = (k + 1u == hole) ? (uint8_t)b : (uint8_t)lds_u8(pool_abs + src + k);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}

@@ -614,6 +614,7 @@ __global__ void k_copy_tail(const uint8_t *__restrict__ src, uint32_t len, uint8
 }
 
 #include "kex_fast.cuh"
+#include "kex_v3.cuh"
 
 // =================================================================== host
 struct PhaseHost {
@@ -636,6 +637,12 @@ struct PhaseHost {
   uint32_t stage_bytes = 12288;       // emit staging window; grows with the observed out/in ratio
   int ef_ctas_per_sm = 0;
   uint32_t ef_stage_cfg = 0;          // stage_bytes the occupancy was computed for
+  // warp-autonomous kernels (kex_v3.cuh); absent -> kex_fast.cuh kernels
+  V3Dev v3;
+  void *d_v3 = nullptr;               // be3, tpl2, fwdtab
+  size_t smem_fwd3 = 0, smem_seams3 = 0;
+  uint32_t v3_stage = 3072;           // per-warp staging window; follows the observed out/in ratio
+  size_t tile() const { return v3.ok ? (size_t)V3_TILE : (size_t)KEX_CHUNK; }
 };
 
 struct Buf {
@@ -693,6 +700,96 @@ static uint32_t rd32(const uint8_t *b, size_t off) {
   return v;
 }
 
+
+// Derived tables of the warp-autonomous kernels (kex_v3.cuh).  Programs whose
+// tables exceed the kernels' packed fields stay on the kex_fast.cuh kernels.
+static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const uint32_t *BE, const uint32_t *tplinfo,
+                   uint32_t NM) {
+  V3Dev &v = ph.v3;
+  memset(&v, 0, sizeof(v));
+  if (getenv("KEX_NO_V3")) return KEX_OK;
+  const FastDev &F = ph.fdev;
+  const uint32_t Q1 = ph.dev.Q + 1, C = ph.dev.C, A = ph.dev.A, NL = F.NL, NB = F.NB, NE = NL * A;
+  if ((NL - 1) * A > 255 || NB > 64 || F.NG > 127) return KEX_OK;
+  // emission entries
+  std::vector<uint32_t> be3(NE), tpl2(NE, 0);
+  for (uint32_t i = 0; i < NE; ++i) {
+    const uint32_t e = BE[i];
+    const uint32_t lamA = (e & 0xFFFCu) / 4u, len = (e >> 16) & 0xFFu;      // lam_before * A
+    uint32_t S = 0, T = 0;
+    if (e & 1u) {
+      S = 1;
+    } else if (e & 2u) {
+      const uint32_t t = e >> 24, src = tplinfo[2 * t] & 0xFFFFu, hm = tplinfo[2 * t + 1];
+      if (hm & (hm - 1u)) return KEX_OK;              // more than one hole
+      uint32_t hole = 0;
+      while (hm >> hole) ++hole;                      // hole offset + 1, 0 = none
+      T = 1;
+      tpl2[i] = src | (len << 16) | (hole << 24);
+    }
+    be3[i] = len | (T << 15) | (S << 16) | (lamA << 24);
+  }
+  // replicated tables must be addressable with 16 bits (2 KiB allowance for the window base)
+  uint32_t log = 0;
+  for (uint32_t cand : {7u, 5u}) {
+    const size_t end = (((size_t)NB * 256 + 127) & ~(size_t)127) + ((size_t)Q1 * C + NE) * (1u << cand);
+    if (end + 2048 <= 65536) { log = cand; break; }
+  }
+  if (!log) return KEX_OK;
+  const uint32_t stride = 1u << log;
+  v.log = log;
+  v.NE = NE;
+  uint32_t sp = 0;
+  v.o_mulB = sp; sp += NB * 256u;
+  sp = (sp + 127u) & ~127u;
+  v.o_trans = sp; sp += Q1 * C * stride;
+  v.o_BE = sp; sp += NE * stride;
+  sp = (sp + 255u) & ~255u;
+  v.o_cls = sp; sp += 256;
+  v.o_compB = sp; sp += NB * NB;
+  v.o_applyB = sp; sp += NB * NL;
+  sp = (sp + 3u) & ~3u;
+  v.o_tpl2 = sp; sp += NE * 4u;
+  v.pool_stride = (F.pool_len + 7u) & ~3u;
+  v.o_pool = sp; sp += 4u * v.pool_stride;
+  sp = (sp + 15u) & ~15u;
+  v.o_slots = sp; sp += 256u + 512u;
+  sp = (sp + 127u) & ~127u;
+  v.o_warp = sp;
+  if (sp + 4u * (2048u + 32u + V3_RECCAP * 8u) > 227u * 1024u) return KEX_OK;
+  // forward table: two bytes per lookup when the pair table fits 16-bit row offsets
+  const bool pair = (size_t)NM * C * C * 2 <= 65534 && (C - 1) * C * 2 <= 255;
+  const uint32_t rowlen = pair ? C * C : C;
+  if ((size_t)NM * rowlen * 2 > 65534 || (C - 1) * 2 > 255) return KEX_OK;
+  v.pair = pair ? 1u : 0u;
+  v.rowbytes = rowlen * 2u;
+  v.recip = (uint32_t)(((1ull << 32) + v.rowbytes - 1) / v.rowbytes);
+  for (uint32_t r = 0; r < NM; ++r)
+    if ((uint32_t)(((unsigned long long)(r * v.rowbytes) * v.recip) >> 32) != r) return KEX_OK;
+  std::vector<uint16_t> fwd((size_t)NM * rowlen);
+  for (uint32_t m = 0; m < NM; ++m)
+    for (uint32_t c0 = 0; c0 < C; ++c0) {
+      const uint32_t m1 = mulF[m * C + c0];
+      if (!pair) { fwd[(size_t)m * C + c0] = (uint16_t)(m1 * v.rowbytes); continue; }
+      for (uint32_t c1 = 0; c1 < C; ++c1) fwd[(size_t)m * rowlen + c0 * C + c1] = (uint16_t)(mulF[m1 * C + c1] * v.rowbytes);
+    }
+  v.fwd_entries = (uint32_t)fwd.size();
+  ph.smem_fwd3 = 512 + ((fwd.size() * 2 + 15) & ~(size_t)15);
+  ph.smem_seams3 = 256 + 4ull * Q1 * C + (size_t)NB * F.NG + NB + 16;
+  if (ph.smem_fwd3 > 200 * 1024 || ph.smem_seams3 > 200 * 1024) return KEX_OK;
+  const size_t o_be = 0, o_tp = o_be + 4ull * NE, o_fw = (o_tp + 4ull * NE + 15) & ~(size_t)15, tot = o_fw + fwd.size() * 2;
+  std::vector<uint8_t> img(tot, 0);
+  memcpy(img.data() + o_be, be3.data(), 4ull * NE);
+  memcpy(img.data() + o_tp, tpl2.data(), 4ull * NE);
+  memcpy(img.data() + o_fw, fwd.data(), fwd.size() * 2);
+  CK(cudaMalloc(&ph.d_v3, tot));
+  CK(cudaMemcpy(ph.d_v3, img.data(), tot, cudaMemcpyHostToDevice));
+  v.be3 = (const uint32_t *)((const uint8_t *)ph.d_v3 + o_be);
+  v.tpl2 = (const uint32_t *)((const uint8_t *)ph.d_v3 + o_tp);
+  v.fwdtab = (const uint16_t *)((const uint8_t *)ph.d_v3 + o_fw);
+  v.ok = 1;
+  return KEX_OK;
+}
 
 // Fast section (fasttab.py): monoid tables.  Malformed -> KEX_ERR_BAD_BLOB;
 // tables too large for shared memory -> the phase stays on the generic kernels.
@@ -760,7 +857,7 @@ static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph
   d.pool = db + off[10];
   ph.smem_ef_tables = tables;
   ph.fast = true;
-  return KEX_OK;
+  return load_v3(p, ph, mulF, BE, tplinfo, NM);
 }
 
 static int load_phase(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
@@ -877,6 +974,13 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
   cudaFuncSetAttribute(k_fwd_monoid, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_emit_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_emit_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k3_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k3_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k3_seams, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k3_emit<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  cudaFuncSetAttribute(k3_emit<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  cudaFuncSetAttribute(k3_emit<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  cudaFuncSetAttribute(k3_emit<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
   if (cudaMallocHost((void **)&p->ctl_host, sizeof(FastCtl)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
   if (cudaMallocHost((void **)&p->res_host, sizeof(RunResult)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
@@ -889,7 +993,7 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
 extern "C" void kex_free(kex_program *p) {
   if (!p) return;
   cudaSetDevice(p->device);
-  for (auto &ph : p->phases) { cudaFree(ph.d_blob); cudaFree(ph.d_extra); }
+  for (auto &ph : p->phases) { cudaFree(ph.d_blob); cudaFree(ph.d_extra); cudaFree(ph.d_v3); }
   for (int i = 0; i < 8; ++i) { cudaFree(p->maps[i].p); cudaFree(p->starts[i].p); cudaFree(p->fates[i].p); cudaFree(p->lives[i].p); }
   Buf *bs[] = {&p->samples, &p->pend, &p->resolved, &p->fail, &p->outlen, &p->outoff, &p->bsum, &p->res_dev,
                &p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out, &p->desc, &p->ctl};
@@ -906,7 +1010,7 @@ extern "C" int kex_info(const kex_program *p, uint32_t phase, kex_info_t *info) 
   const PhaseDev &d = p->phases[phase].dev;
   info->nphases = (uint32_t)p->phases.size();
   info->nstates = d.Q; info->nclasses = d.C; info->nregs = d.R; info->nactions = d.A;
-  info->max_out_per_byte = d.max_out; info->chunk_bytes = KEX_CHUNK;
+  info->max_out_per_byte = d.max_out; info->chunk_bytes = (uint32_t)p->phases[phase].tile();
   info->monoid_kernels = p->phases[phase].fast ? 1u : 0u;
   return KEX_OK;
 }
@@ -1162,10 +1266,27 @@ static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in
     if ((rc = ensure(p, p->starts[l], p->lvl_count[l] * sizeof(uint16_t)))) return rc;
   }
   if ((rc = ensure(p, p->res_dev, sizeof(RunResult)))) return rc;
-  if ((rc = ensure(p, p->samples, nchunks * KEX_NT * sizeof(uint16_t)))) return rc;
+  if ((rc = ensure(p, p->samples, nchunks * (ph.v3.ok ? V3_SPC : KEX_NT) * sizeof(uint16_t)))) return rc;
   if (p->timing) CK(cudaEventRecord(p->ev[0], st));
-  k_fwd_monoid<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_fm, st>>>(P, ph.fdev, d_in, n, nchunks,
-                                                                          (uint16_t *)p->samples.p, (uint16_t *)p->maps[0].p);
+  if (ph.v3.ok) {
+    // two chunks per thread, grid-stride over resident CTAs (the table is staged once per CTA)
+    const size_t npairs = (nchunks + 1) / 2;
+    const unsigned ft = npairs >= 512u * (size_t)p->num_sms ? 512u : 128u;     // small inputs: spread over the SMs
+    size_t ctas = (npairs + ft - 1) / ft;
+    size_t per_sm = (size_t)V3_SMEM_MAX / (ph.smem_fwd3 + 1024);
+    if (per_sm > 2048u / ft) per_sm = 2048u / ft;
+    const size_t resident = (size_t)p->num_sms * (per_sm < 1 ? 1 : per_sm);
+    if (ctas > resident) ctas = resident;
+    if (ph.v3.pair)
+      k3_fwd<true><<<(unsigned)ctas, ft, ph.smem_fwd3, st>>>(P, ph.fdev, ph.v3, d_in, n, nchunks, (uint16_t *)p->samples.p,
+                                                             (uint16_t *)p->maps[0].p);
+    else
+      k3_fwd<false><<<(unsigned)ctas, ft, ph.smem_fwd3, st>>>(P, ph.fdev, ph.v3, d_in, n, nchunks, (uint16_t *)p->samples.p,
+                                                              (uint16_t *)p->maps[0].p);
+  } else {
+    k_fwd_monoid<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_fm, st>>>(P, ph.fdev, d_in, n, nchunks,
+                                                                            (uint16_t *)p->samples.p, (uint16_t *)p->maps[0].p);
+  }
   p->launches++;
   if (p->timing) CK(cudaEventRecord(p->ev[1], st));
   const unsigned bt = Q1 < 32 ? 32 : (Q1 > 256 ? 256 : ((Q1 + 31) / 32 * 32));
@@ -1194,6 +1315,17 @@ static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st) {
     p->launches++;
   }
   int rc;
+  if (ph.v3.ok) {
+    const size_t ntiles = (n + V3_TILE - 1) / V3_TILE;
+    if ((rc = ensure(p, p->bmaps[0], ntiles * NL))) return rc;
+    CK(cudaMemsetAsync(p->res_dev.p, 0xFF, sizeof(unsigned long long), st));     // fail_pos = none
+    if (p->timing) CK(cudaEventRecord(p->ev[2], st));
+    k3_seams<<<(unsigned)((ntiles + 255) / 256), 256, ph.smem_seams3, st>>>(
+        P, ph.fdev, p->sh_in, n, ntiles, (const uint16_t *)p->samples.p, (const uint16_t *)p->starts[0].p,
+        (const uint16_t *)p->maps[0].p, (uint8_t *)p->bmaps[0].p, (RunResult *)p->res_dev.p);
+    p->launches++;
+    if (p->timing) CK(cudaEventRecord(p->ev[3], st));
+  } else {
   if ((rc = ensure(p, p->fail, nchunks * sizeof(uint32_t)))) return rc;
   if ((rc = ensure(p, p->bmaps[0], nchunks * NL))) return rc;
   if (p->timing) CK(cudaEventRecord(p->ev[2], st));
@@ -1204,6 +1336,7 @@ static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st) {
   if (p->timing) CK(cudaEventRecord(p->ev[3], st));
   k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->fail.p, nchunks, (RunResult *)p->res_dev.p);
   p->launches++;
+  }
   CK(cudaMemcpyAsync(p->res_host, p->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return KEX_OK;
@@ -1230,7 +1363,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
   *out_len = 0;
   if (n_eff == 0) return KEX_OK;
   if (lam_end >= NL || ((uintptr_t)d_out & 15u) != 0) return KEX_ERR_ARG;
-  const size_t ntiles = (n_eff + KEX_CHUNK - 1) / KEX_CHUNK;
+  const size_t ntiles = (n_eff + ph.tile() - 1) / ph.tile();
   if (ntiles >= 0xFFFFFFFFull) return KEX_ERR_UNSUPPORTED;
   int rc;
   size_t cnt[8];
@@ -1254,6 +1387,58 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
   if ((rc = ensure(p, p->ctl, sizeof(FastCtl)))) return rc;
   CK(cudaMemsetAsync(p->desc.p, 0, ntiles * 8, st));
   CK(cudaMemsetAsync(p->ctl.p, 0, sizeof(FastCtl), st));
+  if (ph.v3.ok) {
+    // one CTA per SM: up to 31 worker warps + 1 scan warp (as many workers as the
+    // staging windows leave room for); every CTA must be resident because groups
+    // are assigned statically and chained in order
+    const V3Dev &V = ph.v3;
+    const uint32_t warp_bytes = (ph.v3_stage + 32u + V3_RECCAP * 8u + 15u) & ~15u;
+    uint32_t nwork = (uint32_t)(((size_t)V3_SMEM_MAX - V.o_warp) / warp_bytes);
+    if (nwork > 31u) nwork = 31u;
+    if (const char *e = getenv("KEX_V3_WORKERS")) { const uint32_t x = (uint32_t)atoi(e); if (x >= 1 && x < nwork) nwork = x; }
+    if (nwork < 1u) return KEX_ERR_UNSUPPORTED;
+    const size_t smem3 = (size_t)V.o_warp + (size_t)nwork * warp_bytes;
+    const uint32_t nwarp = nwork + 1u;
+    int occ = 0;
+    if (V.log == 7) {
+      if (NL > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<7, true>, (int)(nwarp * 32u), smem3));
+      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<7, false>, (int)(nwarp * 32u), smem3));
+    } else {
+      if (NL > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<5, true>, (int)(nwarp * 32u), smem3));
+      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<5, false>, (int)(nwarp * 32u), smem3));
+    }
+    if (occ < 1) return KEX_ERR_UNSUPPORTED;
+    const size_t ngroups = (ntiles + nwork - 1) / nwork;
+    size_t ctas = ngroups;
+    if (ctas > (size_t)occ * (size_t)p->num_sms) ctas = (size_t)occ * (size_t)p->num_sms;
+    if (p->timing) CK(cudaEventRecord(p->ev[4], st));
+#define V3_LAUNCH(LOGV, REGSV)                                                                                      \
+    k3_emit<LOGV, REGSV><<<(unsigned)ctas, nwarp * 32u, smem3, st>>>(                                               \
+        P, ph.fdev, V, p->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->samples.p,                           \
+        (const uint16_t *)p->starts[0].p, (const uint8_t *)p->lams[0].p, (unsigned long long *)p->desc.p,           \
+        (FastCtl *)p->ctl.p, d_out, out_cap, ph.v3_stage, warp_bytes)
+    if (V.log == 7) { if (NL > 1) V3_LAUNCH(7, true); else V3_LAUNCH(7, false); }
+    else { if (NL > 1) V3_LAUNCH(5, true); else V3_LAUNCH(5, false); }
+#undef V3_LAUNCH
+    p->launches++;
+    if (p->timing) CK(cudaEventRecord(p->ev[5], st));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(p->ctl_host, p->ctl.p, sizeof(FastCtl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (p->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
+    const size_t total = (size_t)p->ctl_host->total_out;
+    *out_len = total;
+    if (p->ctl_host->overflow || total > out_cap) return KEX_ERR_OUT_CAP;
+    // size the staging windows for the next run from the observed out/in ratio
+    const double per_tile = (double)total / (double)ntiles;
+    uint32_t want = (uint32_t)(per_tile * 1.25) + 256;
+    want = (want + 255u) & ~255u;
+    if (want < 2048u) want = 2048u;
+    const uint32_t stage_max = (uint32_t)(((V3_SMEM_MAX - V.o_warp) / 8u - 32u - V3_RECCAP * 8u) & ~255u);   // keep >= 8 warps
+    if (want > stage_max) want = stage_max;
+    if (want > ph.v3_stage || want + 1024u < ph.v3_stage) ph.v3_stage = want;
+    return KEX_OK;
+  }
   const size_t smem = ph.smem_ef_tables + KEX_CHUNK + ph.stage_bytes + 32 + EF_RECCAP * 4 + 16;
   if (ph.ef_ctas_per_sm == 0 || ph.ef_stage_cfg != ph.stage_bytes) {
     int occ = 0;
@@ -1341,7 +1526,8 @@ extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *en
   *fail_pos = (f == KEX_NONE64) ? (size_t)-1 : (size_t)f;
   *end_state = p->res_host->end_state;
   const size_t n_eff = (f == KEX_NONE64) ? p->sh_n : (size_t)f;
-  const size_t nchunks_eff = (n_eff + KEX_CHUNK - 1) / KEX_CHUNK;
+  const size_t unit = ph.fast ? ph.tile() : (size_t)KEX_CHUNK;
+  const size_t nchunks_eff = (n_eff + unit - 1) / unit;
   if (!ph.fast) return do_fate_up(p, nchunks_eff, h_seam, st);
   if (nseam == 1 || nchunks_eff == 0) {
     for (uint32_t r = 0; r < nseam; ++r) h_seam[r] = (uint8_t)r;
