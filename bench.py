@@ -37,7 +37,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons; started before the warm-up so that it
+    is already polling when the timed region begins, `mark()` brackets the region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -46,24 +47,33 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.rows = []
         self.proc = None
+        self.lo = 0
+        self.hi = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
         except Exception:
             pass
 
+    def mark(self, end=False):
+        if end:
+            self.hi = len(self.rows)
+        else:
+            self.lo = len(self.rows)
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.lo:self.hi] or self.rows[max(0, self.lo - 1):(self.hi or 0) + 1]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -167,11 +177,11 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--gib", type=float, default=16.0, help="input GiB per GPU")
-    ap.add_argument("--e2e-gib", type=float, default=1.0, help="host-buffer wave size for the e2e leg")
+    ap.add_argument("--e2e-gib", type=float, default=4.0, help="host buffer size of one kex_run_host call in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -240,14 +250,15 @@ def main():
 
     step = step_single if world == 1 else step_sharded
 
-    for _ in range(args.warmup):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kms = [0.0, 0.0, 0.0, 0.0]
     launches = 0
@@ -259,6 +270,7 @@ def main():
             kms = [a + b for a, b in zip(kms, k)]
     ev1.record()
     torch.cuda.synchronize()
+    sampler.mark(end=True)
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
@@ -306,7 +318,8 @@ def main():
         dt = float(t.item())
     e2e = {"value": world * waves * wave_n * e2e_steps / GIB / dt, "unit": "GiB/s",
            "h2d_bytes_per_step": waves * wave_n, "d2h_bytes_per_step": waves * wave_out,
-           "note": "kex_run_host over pinned host buffers, %d waves of %.2f GiB per step, %d steps" % (
+           "note": "kex_run_host over pinned host buffers, %d calls of %.2f GiB per step, %d steps; inside a call "
+                   "128 MiB sub-waves are copied in, evaluated and copied out on three streams" % (
                waves, wave_n / GIB, e2e_steps)}
 
     if rank == 0:

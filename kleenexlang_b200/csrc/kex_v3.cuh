@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(1024, 1)
 k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
         const uint16_t *__restrict__ samples, const uint16_t *__restrict__ chunk_start,
         const uint8_t *__restrict__ lam_end, unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl,
-        uint8_t *__restrict__ out, size_t out_cap, uint32_t stage_bytes, uint32_t warp_bytes) {
+        uint8_t *__restrict__ out, size_t out_cap, unsigned long long out_off, uint32_t stage_bytes,
+        uint32_t warp_bytes) {
   constexpr uint32_t STRIDE = 1u << LOG, REP = STRIDE / 4u;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const uint32_t Q = P.Q, Q1 = Q + 1, C = P.C, A = P.A, NL = F.NL, NB = F.NB, NG = F.NG;
@@ -488,7 +489,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
         st_desc(desc + grp, EF_FLAG_INC | (gex + gsum));
         if (grp == ngroups - 1) ctl->total_out = gex + gsum;
       }
-      bases[par * 32u + lane] = gex + (unsigned long long)(inc_s - tv);
+      bases[par * 32u + lane] = out_off + gex + (unsigned long long)(inc_s - tv);
       __threadfence_block();
       asm volatile("bar.arrive 2, %0;" ::"r"(bar_n) : "memory");
     }

@@ -650,6 +650,23 @@ struct Buf {
   size_t cap = 0;
 };
 
+// Scratch of one run / shard in flight (grow-only device buffers and the state
+// carried between the shard steps).  A program holds two so that the host
+// pipeline of kex_run_host can walk one sub-wave while the previous one emits.
+struct Ctx {
+  Buf maps[8], starts[8], fates[8], lives[8];
+  Buf samples, pend, resolved, fail, outlen, outoff, bsum, res_dev;
+  Buf bmaps[8], lams[8], desc, ctl;
+  FastCtl *ctl_host = nullptr;
+  RunResult *res_host = nullptr;
+  // shard state between the three shard calls
+  const uint8_t *sh_in = nullptr;
+  size_t sh_n = 0, sh_nchunks = 0;
+  size_t lvl_count[8];
+  int nlevels = 0;
+  uint32_t sh_phase = 0;
+};
+
 struct kex_program {
   int device = 0;
   std::vector<PhaseHost> phases;
@@ -659,19 +676,14 @@ struct kex_program {
   float ms[4] = {0, 0, 0, 0};
   cudaEvent_t ev[8];
   bool ev_ok = false;
-  // scratch (grow-only)
-  Buf maps[8], starts[8], fates[8], lives[8];
-  Buf samples, pend, resolved, fail, outlen, outoff, bsum, res_dev, inter[2], hostio_in, hostio_out;
-  Buf bmaps[8], lams[8], desc, ctl;
-  FastCtl *ctl_host = nullptr;
+  Ctx cx[2];
+  Ctx *c = &cx[0];
+  Buf inter[2], hostio_in, hostio_out;
   int num_sms = 0;
-  RunResult *res_host = nullptr;
-  // shard state between the three shard calls
-  const uint8_t *sh_in = nullptr;
-  size_t sh_n = 0, sh_nchunks = 0;
-  size_t lvl_count[8];
-  int nlevels = 0;
-  uint32_t sh_phase = 0;
+  // host pipeline (kex_run_host)
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> pipe_ev;
+  size_t emit_out_off = 0;            // v3 emit: offset of this shard's output inside d_out
 };
 
 #define CK(call)                                                              \
@@ -982,8 +994,10 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
   cudaFuncSetAttribute(k3_emit<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
   cudaFuncSetAttribute(k3_emit<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
-  if (cudaMallocHost((void **)&p->ctl_host, sizeof(FastCtl)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
-  if (cudaMallocHost((void **)&p->res_host, sizeof(RunResult)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
+  for (Ctx &c : p->cx) {
+    if (cudaMallocHost((void **)&c.ctl_host, sizeof(FastCtl)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
+    if (cudaMallocHost((void **)&c.res_host, sizeof(RunResult)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
+  }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&p->ev[i]);
   p->ev_ok = true;
   *out = p;
@@ -994,13 +1008,21 @@ extern "C" void kex_free(kex_program *p) {
   if (!p) return;
   cudaSetDevice(p->device);
   for (auto &ph : p->phases) { cudaFree(ph.d_blob); cudaFree(ph.d_extra); cudaFree(ph.d_v3); }
-  for (int i = 0; i < 8; ++i) { cudaFree(p->maps[i].p); cudaFree(p->starts[i].p); cudaFree(p->fates[i].p); cudaFree(p->lives[i].p); }
-  Buf *bs[] = {&p->samples, &p->pend, &p->resolved, &p->fail, &p->outlen, &p->outoff, &p->bsum, &p->res_dev,
-               &p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out, &p->desc, &p->ctl};
-  for (int i = 0; i < 8; ++i) { cudaFree(p->bmaps[i].p); cudaFree(p->lams[i].p); }
-  if (p->ctl_host) cudaFreeHost(p->ctl_host);
-  for (Buf *b : bs) cudaFree(b->p);
-  if (p->res_host) cudaFreeHost(p->res_host);
+  for (Ctx &c : p->cx) {
+    for (int i = 0; i < 8; ++i) {
+      cudaFree(c.maps[i].p); cudaFree(c.starts[i].p); cudaFree(c.fates[i].p); cudaFree(c.lives[i].p);
+      cudaFree(c.bmaps[i].p); cudaFree(c.lams[i].p);
+    }
+    Buf *bs[] = {&c.samples, &c.pend, &c.resolved, &c.fail, &c.outlen, &c.outoff, &c.bsum, &c.res_dev, &c.desc, &c.ctl};
+    for (Buf *b : bs) cudaFree(b->p);
+    if (c.ctl_host) cudaFreeHost(c.ctl_host);
+    if (c.res_host) cudaFreeHost(c.res_host);
+  }
+  for (Buf *b : {&p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out}) cudaFree(b->p);
+  if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
+  if (p->s_comp) cudaStreamDestroy(p->s_comp);
+  if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
+  for (cudaEvent_t e : p->pipe_ev) cudaEventDestroy(e);
   if (p->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(p->ev[i]);
   delete p;
 }
@@ -1024,7 +1046,7 @@ static uint32_t final_code(const PhaseHost &ph, uint32_t state) {
 extern "C" int kex_final_action(const kex_program *p, uint32_t state, int *accepting, uint32_t *seam_code,
                                 const uint8_t **tail, size_t *tail_len) {
   if (!p) return KEX_ERR_ARG;
-  const PhaseHost &ph = p->phases[p->sh_phase];
+  const PhaseHost &ph = p->phases[p->c->sh_phase];
   if (state > ph.dev.Q) return KEX_ERR_ARG;
   const int32_t a = ph.fin[state];
   if (accepting) *accepting = a >= 0;
@@ -1081,33 +1103,33 @@ static int do_summarize(kex_program *p, uint32_t phase, const uint8_t *d_in, siz
   const PhaseDev &P = ph.dev;
   const uint32_t Q1 = P.Q + 1;
   if (((uintptr_t)d_in & 15u) != 0) return KEX_ERR_ARG;
-  p->sh_in = d_in; p->sh_n = n; p->sh_phase = phase;
+  p->c->sh_in = d_in; p->c->sh_n = n; p->c->sh_phase = phase;
   const size_t nchunks = (n + KEX_CHUNK - 1) / KEX_CHUNK;
-  p->sh_nchunks = nchunks;
+  p->c->sh_nchunks = nchunks;
   // level sizes
-  p->nlevels = 0;
+  p->c->nlevels = 0;
   size_t c = nchunks;
   while (true) {
-    p->lvl_count[p->nlevels++] = c;
+    p->c->lvl_count[p->c->nlevels++] = c;
     if (c <= 1) break;
     c = (c + KEX_FANIN - 1) / KEX_FANIN;
   }
-  for (int l = 0; l < p->nlevels; ++l) {
-    int rc = ensure(p, p->maps[l], p->lvl_count[l] * Q1 * sizeof(uint16_t));
+  for (int l = 0; l < p->c->nlevels; ++l) {
+    int rc = ensure(p, p->c->maps[l], p->c->lvl_count[l] * Q1 * sizeof(uint16_t));
     if (rc) return rc;
-    rc = ensure(p, p->starts[l], p->lvl_count[l] * sizeof(uint16_t));
+    rc = ensure(p, p->c->starts[l], p->c->lvl_count[l] * sizeof(uint16_t));
     if (rc) return rc;
   }
-  int rc = ensure(p, p->res_dev, sizeof(RunResult));
+  int rc = ensure(p, p->c->res_dev, sizeof(RunResult));
   if (rc) return rc;
   if (p->timing) CK(cudaEventRecord(p->ev[0], st));
-  k_chunk_maps<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_maps, st>>>(P, d_in, n, nchunks, (uint16_t *)p->maps[0].p);
+  k_chunk_maps<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_maps, st>>>(P, d_in, n, nchunks, (uint16_t *)p->c->maps[0].p);
   p->launches++;
   if (p->timing) CK(cudaEventRecord(p->ev[1], st));
   const unsigned bt = Q1 < 32 ? 32 : (Q1 > 256 ? 256 : ((Q1 + 31) / 32 * 32));
-  for (int l = 1; l < p->nlevels; ++l) {
-    k_compose<uint16_t, false><<<(unsigned)p->lvl_count[l], bt, 0, st>>>((const uint16_t *)p->maps[l - 1].p, p->lvl_count[l - 1],
-                                                                       (uint16_t *)p->maps[l].p, Q1);
+  for (int l = 1; l < p->c->nlevels; ++l) {
+    k_compose<uint16_t, false><<<(unsigned)p->c->lvl_count[l], bt, 0, st>>>((const uint16_t *)p->c->maps[l - 1].p, p->c->lvl_count[l - 1],
+                                                                       (uint16_t *)p->c->maps[l].p, Q1);
     p->launches++;
   }
   CK(cudaGetLastError());
@@ -1115,44 +1137,44 @@ static int do_summarize(kex_program *p, uint32_t phase, const uint8_t *d_in, siz
 }
 
 static int do_walk(kex_program *p, uint32_t start_state, cudaStream_t st) {
-  PhaseHost &ph = p->phases[p->sh_phase];
+  PhaseHost &ph = p->phases[p->c->sh_phase];
   if (ph.fast) return do_walk_fast(p, start_state, st);
   const PhaseDev &P = ph.dev;
   const uint32_t Q1 = P.Q + 1, R = P.R;
-  const size_t nchunks = p->sh_nchunks, n = p->sh_n;
-  const int top = p->nlevels - 1;
-  k_set_u16<<<1, 1, 0, st>>>((uint16_t *)p->starts[top].p, start_state);
+  const size_t nchunks = p->c->sh_nchunks, n = p->c->sh_n;
+  const int top = p->c->nlevels - 1;
+  k_set_u16<<<1, 1, 0, st>>>((uint16_t *)p->c->starts[top].p, start_state);
   p->launches++;
   for (int l = top; l >= 1; --l) {
-    const size_t np = p->lvl_count[l];
-    k_push_states<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const uint16_t *)p->maps[l - 1].p, p->lvl_count[l - 1],
-                                                                (const uint16_t *)p->starts[l].p, np,
-                                                                (uint16_t *)p->starts[l - 1].p, Q1);
+    const size_t np = p->c->lvl_count[l];
+    k_push_states<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const uint16_t *)p->c->maps[l - 1].p, p->c->lvl_count[l - 1],
+                                                                (const uint16_t *)p->c->starts[l].p, np,
+                                                                (uint16_t *)p->c->starts[l - 1].p, Q1);
     p->launches++;
   }
   int rc;
   const size_t nsamp = nchunks * KEX_NT;
-  if ((rc = ensure(p, p->samples, nsamp * sizeof(uint16_t)))) return rc;
-  if ((rc = ensure(p, p->resolved, nchunks * sizeof(unsigned long long)))) return rc;
-  if ((rc = ensure(p, p->fail, nchunks * sizeof(uint32_t)))) return rc;
-  if ((rc = ensure(p, p->pend, nchunks * R * sizeof(uint32_t)))) return rc;
-  if ((rc = ensure(p, p->fates[0], nchunks * R))) return rc;
+  if ((rc = ensure(p, p->c->samples, nsamp * sizeof(uint16_t)))) return rc;
+  if ((rc = ensure(p, p->c->resolved, nchunks * sizeof(unsigned long long)))) return rc;
+  if ((rc = ensure(p, p->c->fail, nchunks * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(p, p->c->pend, nchunks * R * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(p, p->c->fates[0], nchunks * R))) return rc;
   if (p->timing) CK(cudaEventRecord(p->ev[2], st));
   k_true_walk<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_walk, st>>>(
-      P, p->sh_in, n, nchunks, (const uint16_t *)p->starts[0].p, (uint16_t *)p->samples.p, (uint8_t *)p->fates[0].p,
-      (uint32_t *)p->pend.p, (unsigned long long *)p->resolved.p, (uint32_t *)p->fail.p, (RunResult *)p->res_dev.p);
+      P, p->c->sh_in, n, nchunks, (const uint16_t *)p->c->starts[0].p, (uint16_t *)p->c->samples.p, (uint8_t *)p->c->fates[0].p,
+      (uint32_t *)p->c->pend.p, (unsigned long long *)p->c->resolved.p, (uint32_t *)p->c->fail.p, (RunResult *)p->c->res_dev.p);
   p->launches++;
   if (p->timing) CK(cudaEventRecord(p->ev[3], st));
-  k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->fail.p, nchunks, (RunResult *)p->res_dev.p);
+  k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->c->fail.p, nchunks, (RunResult *)p->c->res_dev.p);
   p->launches++;
-  CK(cudaMemcpyAsync(p->res_host, p->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(p->c->res_host, p->c->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return KEX_OK;
 }
 
 // fate maps of the first `nchunks_eff` chunks -> composed fate map (host, R bytes)
 static int do_fate_up(kex_program *p, size_t nchunks_eff, uint8_t *h_fate, cudaStream_t st) {
-  PhaseHost &ph = p->phases[p->sh_phase];
+  PhaseHost &ph = p->phases[p->c->sh_phase];
   const uint32_t R = ph.dev.R;
   if (R == 1 || nchunks_eff == 0) {
     for (uint32_t r = 0; r < R; ++r) h_fate[r] = (uint8_t)r;
@@ -1163,20 +1185,20 @@ static int do_fate_up(kex_program *p, size_t nchunks_eff, uint8_t *h_fate, cudaS
   size_t c = nchunks_eff;
   while (true) { cnt[nl++] = c; if (c <= 1) break; c = (c + KEX_FANIN - 1) / KEX_FANIN; }
   for (int l = 1; l < nl; ++l) {
-    int rc = ensure(p, p->fates[l], cnt[l] * R);
+    int rc = ensure(p, p->c->fates[l], cnt[l] * R);
     if (rc) return rc;
-    k_compose<uint8_t, true><<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->fates[l - 1].p, cnt[l - 1],
-                                                            (uint8_t *)p->fates[l].p, R);
+    k_compose<uint8_t, true><<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->c->fates[l - 1].p, cnt[l - 1],
+                                                            (uint8_t *)p->c->fates[l].p, R);
     p->launches++;
   }
-  CK(cudaMemcpyAsync(h_fate, p->fates[nl - 1].p, R, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_fate, p->c->fates[nl - 1].p, R, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return KEX_OK;
 }
 
 static int do_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff, uint8_t *d_out, size_t out_cap,
                    size_t *out_len, cudaStream_t st) {
-  PhaseHost &ph = p->phases[p->sh_phase];
+  PhaseHost &ph = p->phases[p->c->sh_phase];
   if (ph.fast) return do_emit_fast(p, live_end_mask, n_eff, d_out, out_cap, out_len, st);
   const PhaseDev &P = ph.dev;
   const uint32_t R = P.R;
@@ -1189,53 +1211,53 @@ static int do_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff, uint8_t
   size_t c = nchunks;
   while (true) { cnt[nl++] = c; if (c <= 1) break; c = (c + KEX_FANIN - 1) / KEX_FANIN; }
   if (R > 1) {
-    for (int l = 0; l < nl; ++l) if ((rc = ensure(p, p->lives[l], cnt[l] * sizeof(uint32_t)))) return rc;
-    for (int l = 1; l < nl; ++l) if ((rc = ensure(p, p->fates[l], cnt[l] * R))) return rc;
+    for (int l = 0; l < nl; ++l) if ((rc = ensure(p, p->c->lives[l], cnt[l] * sizeof(uint32_t)))) return rc;
+    for (int l = 1; l < nl; ++l) if ((rc = ensure(p, p->c->fates[l], cnt[l] * R))) return rc;
     // the up-sweep over exactly these chunks (a failing shard has fewer chunks than it walked)
     for (int l = 1; l < nl; ++l) {
-      k_compose<uint8_t, true><<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->fates[l - 1].p, cnt[l - 1],
-                                                              (uint8_t *)p->fates[l].p, R);
+      k_compose<uint8_t, true><<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->c->fates[l - 1].p, cnt[l - 1],
+                                                              (uint8_t *)p->c->fates[l].p, R);
       p->launches++;
     }
-    k_set_u32<<<1, 1, 0, st>>>((uint32_t *)p->lives[nl - 1].p, live_end_mask);
+    k_set_u32<<<1, 1, 0, st>>>((uint32_t *)p->c->lives[nl - 1].p, live_end_mask);
     p->launches++;
     for (int l = nl - 1; l >= 1; --l) {
-      k_push_live<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, st>>>((const uint8_t *)p->fates[l - 1].p, cnt[l - 1],
-                                                                   (const uint32_t *)p->lives[l].p, cnt[l],
-                                                                   (uint32_t *)p->lives[l - 1].p, R);
+      k_push_live<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, st>>>((const uint8_t *)p->c->fates[l - 1].p, cnt[l - 1],
+                                                                   (const uint32_t *)p->c->lives[l].p, cnt[l],
+                                                                   (uint32_t *)p->c->lives[l - 1].p, R);
       p->launches++;
     }
   } else {
-    if ((rc = ensure(p, p->lives[0], sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(p, p->c->lives[0], sizeof(uint32_t)))) return rc;
   }
-  if ((rc = ensure(p, p->outlen, nchunks * 8))) return rc;
-  if ((rc = ensure(p, p->outoff, (nchunks + 1) * 8))) return rc;
+  if ((rc = ensure(p, p->c->outlen, nchunks * 8))) return rc;
+  if ((rc = ensure(p, p->c->outoff, (nchunks + 1) * 8))) return rc;
   const size_t nb = (nchunks + SCAN_TILE - 1) / SCAN_TILE;
-  if ((rc = ensure(p, p->bsum, nb * 8))) return rc;
-  k_outlen<<<(unsigned)((nchunks + 255) / 256), 256, 0, st>>>((const uint32_t *)p->pend.p, (const unsigned long long *)p->resolved.p,
-                                                             (const uint32_t *)p->lives[0].p, nchunks, R,
-                                                             (unsigned long long *)p->outlen.p);
-  k_scan_sums<<<(unsigned)nb, SCAN_THREADS, 0, st>>>((const unsigned long long *)p->outlen.p, nchunks, (unsigned long long *)p->bsum.p);
-  k_scan_top<<<1, SCAN_THREADS, 0, st>>>((unsigned long long *)p->bsum.p, nb, (RunResult *)p->res_dev.p);
-  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, st>>>((const unsigned long long *)p->outlen.p, nchunks,
-                                                     (const unsigned long long *)p->bsum.p, (unsigned long long *)p->outoff.p);
+  if ((rc = ensure(p, p->c->bsum, nb * 8))) return rc;
+  k_outlen<<<(unsigned)((nchunks + 255) / 256), 256, 0, st>>>((const uint32_t *)p->c->pend.p, (const unsigned long long *)p->c->resolved.p,
+                                                             (const uint32_t *)p->c->lives[0].p, nchunks, R,
+                                                             (unsigned long long *)p->c->outlen.p);
+  k_scan_sums<<<(unsigned)nb, SCAN_THREADS, 0, st>>>((const unsigned long long *)p->c->outlen.p, nchunks, (unsigned long long *)p->c->bsum.p);
+  k_scan_top<<<1, SCAN_THREADS, 0, st>>>((unsigned long long *)p->c->bsum.p, nb, (RunResult *)p->c->res_dev.p);
+  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, st>>>((const unsigned long long *)p->c->outlen.p, nchunks,
+                                                     (const unsigned long long *)p->c->bsum.p, (unsigned long long *)p->c->outoff.p);
   p->launches += 4;
-  CK(cudaMemcpyAsync(p->res_host, p->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(p->c->res_host, p->c->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const size_t total = (size_t)p->res_host->total_out;
+  const size_t total = (size_t)p->c->res_host->total_out;
   *out_len = total;
   if (total > out_cap) return KEX_ERR_OUT_CAP;
   if (p->timing) CK(cudaEventRecord(p->ev[4], st));
   const unsigned grid = (unsigned)nchunks;
   if (ph.mask_bytes == 0)
-    k_emit<0><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->sh_in, n_eff, (const uint16_t *)p->samples.p,
-                                                  (const unsigned long long *)p->outoff.p, (const uint32_t *)p->lives[0].p, d_out);
+    k_emit<0><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->c->sh_in, n_eff, (const uint16_t *)p->c->samples.p,
+                                                  (const unsigned long long *)p->c->outoff.p, (const uint32_t *)p->c->lives[0].p, d_out);
   else if (ph.mask_bytes == 1)
-    k_emit<1><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->sh_in, n_eff, (const uint16_t *)p->samples.p,
-                                                  (const unsigned long long *)p->outoff.p, (const uint32_t *)p->lives[0].p, d_out);
+    k_emit<1><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->c->sh_in, n_eff, (const uint16_t *)p->c->samples.p,
+                                                  (const unsigned long long *)p->c->outoff.p, (const uint32_t *)p->c->lives[0].p, d_out);
   else
-    k_emit<4><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->sh_in, n_eff, (const uint16_t *)p->samples.p,
-                                                  (const unsigned long long *)p->outoff.p, (const uint32_t *)p->lives[0].p, d_out);
+    k_emit<4><<<grid, KEX_NT, ph.smem_emit, st>>>(P, p->c->sh_in, n_eff, (const uint16_t *)p->c->samples.p,
+                                                  (const unsigned long long *)p->c->outoff.p, (const uint32_t *)p->c->lives[0].p, d_out);
   p->launches++;
   if (p->timing) CK(cudaEventRecord(p->ev[5], st));
   CK(cudaGetLastError());
@@ -1256,17 +1278,17 @@ static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in
   const PhaseDev &P = ph.dev;
   const uint32_t Q1 = P.Q + 1;
   if (((uintptr_t)d_in & 15u) != 0) return KEX_ERR_ARG;
-  p->sh_in = d_in; p->sh_n = n; p->sh_phase = phase;
+  p->c->sh_in = d_in; p->c->sh_n = n; p->c->sh_phase = phase;
   const size_t nchunks = (n + KEX_CHUNK - 1) / KEX_CHUNK;
-  p->sh_nchunks = nchunks;
-  level_counts(nchunks, p->lvl_count, &p->nlevels);
+  p->c->sh_nchunks = nchunks;
+  level_counts(nchunks, p->c->lvl_count, &p->c->nlevels);
   int rc;
-  for (int l = 0; l < p->nlevels; ++l) {
-    if ((rc = ensure(p, p->maps[l], p->lvl_count[l] * Q1 * sizeof(uint16_t)))) return rc;
-    if ((rc = ensure(p, p->starts[l], p->lvl_count[l] * sizeof(uint16_t)))) return rc;
+  for (int l = 0; l < p->c->nlevels; ++l) {
+    if ((rc = ensure(p, p->c->maps[l], p->c->lvl_count[l] * Q1 * sizeof(uint16_t)))) return rc;
+    if ((rc = ensure(p, p->c->starts[l], p->c->lvl_count[l] * sizeof(uint16_t)))) return rc;
   }
-  if ((rc = ensure(p, p->res_dev, sizeof(RunResult)))) return rc;
-  if ((rc = ensure(p, p->samples, nchunks * (ph.v3.ok ? V3_SPC : KEX_NT) * sizeof(uint16_t)))) return rc;
+  if ((rc = ensure(p, p->c->res_dev, sizeof(RunResult)))) return rc;
+  if ((rc = ensure(p, p->c->samples, nchunks * (ph.v3.ok ? V3_SPC : KEX_NT) * sizeof(uint16_t)))) return rc;
   if (p->timing) CK(cudaEventRecord(p->ev[0], st));
   if (ph.v3.ok) {
     // two chunks per thread, grid-stride over resident CTAs (the table is staged once per CTA)
@@ -1278,21 +1300,21 @@ static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in
     const size_t resident = (size_t)p->num_sms * (per_sm < 1 ? 1 : per_sm);
     if (ctas > resident) ctas = resident;
     if (ph.v3.pair)
-      k3_fwd<true><<<(unsigned)ctas, ft, ph.smem_fwd3, st>>>(P, ph.fdev, ph.v3, d_in, n, nchunks, (uint16_t *)p->samples.p,
-                                                             (uint16_t *)p->maps[0].p);
+      k3_fwd<true><<<(unsigned)ctas, ft, ph.smem_fwd3, st>>>(P, ph.fdev, ph.v3, d_in, n, nchunks, (uint16_t *)p->c->samples.p,
+                                                             (uint16_t *)p->c->maps[0].p);
     else
-      k3_fwd<false><<<(unsigned)ctas, ft, ph.smem_fwd3, st>>>(P, ph.fdev, ph.v3, d_in, n, nchunks, (uint16_t *)p->samples.p,
-                                                              (uint16_t *)p->maps[0].p);
+      k3_fwd<false><<<(unsigned)ctas, ft, ph.smem_fwd3, st>>>(P, ph.fdev, ph.v3, d_in, n, nchunks, (uint16_t *)p->c->samples.p,
+                                                              (uint16_t *)p->c->maps[0].p);
   } else {
     k_fwd_monoid<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_fm, st>>>(P, ph.fdev, d_in, n, nchunks,
-                                                                            (uint16_t *)p->samples.p, (uint16_t *)p->maps[0].p);
+                                                                            (uint16_t *)p->c->samples.p, (uint16_t *)p->c->maps[0].p);
   }
   p->launches++;
   if (p->timing) CK(cudaEventRecord(p->ev[1], st));
   const unsigned bt = Q1 < 32 ? 32 : (Q1 > 256 ? 256 : ((Q1 + 31) / 32 * 32));
-  for (int l = 1; l < p->nlevels; ++l) {
-    k_compose<uint16_t, false><<<(unsigned)p->lvl_count[l], bt, 0, st>>>((const uint16_t *)p->maps[l - 1].p, p->lvl_count[l - 1],
-                                                                       (uint16_t *)p->maps[l].p, Q1);
+  for (int l = 1; l < p->c->nlevels; ++l) {
+    k_compose<uint16_t, false><<<(unsigned)p->c->lvl_count[l], bt, 0, st>>>((const uint16_t *)p->c->maps[l - 1].p, p->c->lvl_count[l - 1],
+                                                                       (uint16_t *)p->c->maps[l].p, Q1);
     p->launches++;
   }
   CK(cudaGetLastError());
@@ -1300,56 +1322,56 @@ static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in
 }
 
 static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st) {
-  PhaseHost &ph = p->phases[p->sh_phase];
+  PhaseHost &ph = p->phases[p->c->sh_phase];
   const PhaseDev &P = ph.dev;
   const uint32_t Q1 = P.Q + 1, NL = ph.fdev.NL;
-  const size_t nchunks = p->sh_nchunks, n = p->sh_n;
-  const int top = p->nlevels - 1;
-  k_set_u16<<<1, 1, 0, st>>>((uint16_t *)p->starts[top].p, start_state);
+  const size_t nchunks = p->c->sh_nchunks, n = p->c->sh_n;
+  const int top = p->c->nlevels - 1;
+  k_set_u16<<<1, 1, 0, st>>>((uint16_t *)p->c->starts[top].p, start_state);
   p->launches++;
   for (int l = top; l >= 1; --l) {
-    const size_t np = p->lvl_count[l];
-    k_push_states<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const uint16_t *)p->maps[l - 1].p, p->lvl_count[l - 1],
-                                                                (const uint16_t *)p->starts[l].p, np,
-                                                                (uint16_t *)p->starts[l - 1].p, Q1);
+    const size_t np = p->c->lvl_count[l];
+    k_push_states<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const uint16_t *)p->c->maps[l - 1].p, p->c->lvl_count[l - 1],
+                                                                (const uint16_t *)p->c->starts[l].p, np,
+                                                                (uint16_t *)p->c->starts[l - 1].p, Q1);
     p->launches++;
   }
   int rc;
   if (ph.v3.ok) {
     const size_t ntiles = (n + V3_TILE - 1) / V3_TILE;
-    if ((rc = ensure(p, p->bmaps[0], ntiles * NL))) return rc;
-    CK(cudaMemsetAsync(p->res_dev.p, 0xFF, sizeof(unsigned long long), st));     // fail_pos = none
+    if ((rc = ensure(p, p->c->bmaps[0], ntiles * NL))) return rc;
+    CK(cudaMemsetAsync(p->c->res_dev.p, 0xFF, sizeof(unsigned long long), st));     // fail_pos = none
     if (p->timing) CK(cudaEventRecord(p->ev[2], st));
     k3_seams<<<(unsigned)((ntiles + 255) / 256), 256, ph.smem_seams3, st>>>(
-        P, ph.fdev, p->sh_in, n, ntiles, (const uint16_t *)p->samples.p, (const uint16_t *)p->starts[0].p,
-        (const uint16_t *)p->maps[0].p, (uint8_t *)p->bmaps[0].p, (RunResult *)p->res_dev.p);
+        P, ph.fdev, p->c->sh_in, n, ntiles, (const uint16_t *)p->c->samples.p, (const uint16_t *)p->c->starts[0].p,
+        (const uint16_t *)p->c->maps[0].p, (uint8_t *)p->c->bmaps[0].p, (RunResult *)p->c->res_dev.p);
     p->launches++;
     if (p->timing) CK(cudaEventRecord(p->ev[3], st));
   } else {
-  if ((rc = ensure(p, p->fail, nchunks * sizeof(uint32_t)))) return rc;
-  if ((rc = ensure(p, p->bmaps[0], nchunks * NL))) return rc;
+  if ((rc = ensure(p, p->c->fail, nchunks * sizeof(uint32_t)))) return rc;
+  if ((rc = ensure(p, p->c->bmaps[0], nchunks * NL))) return rc;
   if (p->timing) CK(cudaEventRecord(p->ev[2], st));
-  k_seams<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(P, ph.fdev, p->sh_in, n, nchunks, (const uint16_t *)p->starts[0].p,
-                                                            (const uint16_t *)p->maps[0].p, (uint8_t *)p->bmaps[0].p,
-                                                            (uint32_t *)p->fail.p, (RunResult *)p->res_dev.p);
+  k_seams<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(P, ph.fdev, p->c->sh_in, n, nchunks, (const uint16_t *)p->c->starts[0].p,
+                                                            (const uint16_t *)p->c->maps[0].p, (uint8_t *)p->c->bmaps[0].p,
+                                                            (uint32_t *)p->c->fail.p, (RunResult *)p->c->res_dev.p);
   p->launches++;
   if (p->timing) CK(cudaEventRecord(p->ev[3], st));
-  k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->fail.p, nchunks, (RunResult *)p->res_dev.p);
+  k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->c->fail.p, nchunks, (RunResult *)p->c->res_dev.p);
   p->launches++;
   }
-  CK(cudaMemcpyAsync(p->res_host, p->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(p->c->res_host, p->c->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return KEX_OK;
 }
 
 // backward up-sweep over the first nchunks_eff chunk maps; returns the level count
 static int lam_up(kex_program *p, size_t nchunks_eff, size_t *cnt, int *nl, cudaStream_t st) {
-  const uint32_t NL = p->phases[p->sh_phase].fdev.NL;
+  const uint32_t NL = p->phases[p->c->sh_phase].fdev.NL;
   level_counts(nchunks_eff, cnt, nl);
   for (int l = 1; l < *nl; ++l) {
-    int rc = ensure(p, p->bmaps[l], cnt[l] * NL);
+    int rc = ensure(p, p->c->bmaps[l], cnt[l] * NL);
     if (rc) return rc;
-    k_compose_rev<<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->bmaps[l - 1].p, cnt[l - 1], (uint8_t *)p->bmaps[l].p, NL);
+    k_compose_rev<<<(unsigned)cnt[l], 32, 0, st>>>((const uint8_t *)p->c->bmaps[l - 1].p, cnt[l - 1], (uint8_t *)p->c->bmaps[l].p, NL);
     p->launches++;
   }
   return KEX_OK;
@@ -1357,7 +1379,7 @@ static int lam_up(kex_program *p, size_t nchunks_eff, size_t *cnt, int *nl, cuda
 
 static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t *d_out, size_t out_cap, size_t *out_len,
                         cudaStream_t st) {
-  PhaseHost &ph = p->phases[p->sh_phase];
+  PhaseHost &ph = p->phases[p->c->sh_phase];
   const PhaseDev &P = ph.dev;
   const uint32_t NL = ph.fdev.NL;
   *out_len = 0;
@@ -1371,22 +1393,22 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
   level_counts(ntiles, cnt, &nl);
   if (NL > 1) {
     if ((rc = lam_up(p, ntiles, cnt, &nl, st))) return rc;
-    for (int l = 0; l < nl; ++l) if ((rc = ensure(p, p->lams[l], cnt[l]))) return rc;
-    k_set_u8<<<1, 1, 0, st>>>((uint8_t *)p->lams[nl - 1].p, lam_end);
+    for (int l = 0; l < nl; ++l) if ((rc = ensure(p, p->c->lams[l], cnt[l]))) return rc;
+    k_set_u8<<<1, 1, 0, st>>>((uint8_t *)p->c->lams[nl - 1].p, lam_end);
     p->launches++;
     for (int l = nl - 1; l >= 1; --l) {
-      k_push_lam<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, st>>>((const uint8_t *)p->bmaps[l - 1].p, cnt[l - 1],
-                                                                  (const uint8_t *)p->lams[l].p, cnt[l],
-                                                                  (uint8_t *)p->lams[l - 1].p, NL);
+      k_push_lam<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, st>>>((const uint8_t *)p->c->bmaps[l - 1].p, cnt[l - 1],
+                                                                  (const uint8_t *)p->c->lams[l].p, cnt[l],
+                                                                  (uint8_t *)p->c->lams[l - 1].p, NL);
       p->launches++;
     }
   } else {
-    if ((rc = ensure(p, p->lams[0], 16))) return rc;
+    if ((rc = ensure(p, p->c->lams[0], 16))) return rc;
   }
-  if ((rc = ensure(p, p->desc, ntiles * 8))) return rc;
-  if ((rc = ensure(p, p->ctl, sizeof(FastCtl)))) return rc;
-  CK(cudaMemsetAsync(p->desc.p, 0, ntiles * 8, st));
-  CK(cudaMemsetAsync(p->ctl.p, 0, sizeof(FastCtl), st));
+  if ((rc = ensure(p, p->c->desc, ntiles * 8))) return rc;
+  if ((rc = ensure(p, p->c->ctl, sizeof(FastCtl)))) return rc;
+  CK(cudaMemsetAsync(p->c->desc.p, 0, ntiles * 8, st));
+  CK(cudaMemsetAsync(p->c->ctl.p, 0, sizeof(FastCtl), st));
   if (ph.v3.ok) {
     // one CTA per SM: up to 31 worker warps + 1 scan warp (as many workers as the
     // staging windows leave room for); every CTA must be resident because groups
@@ -1414,21 +1436,21 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     if (p->timing) CK(cudaEventRecord(p->ev[4], st));
 #define V3_LAUNCH(LOGV, REGSV)                                                                                      \
     k3_emit<LOGV, REGSV><<<(unsigned)ctas, nwarp * 32u, smem3, st>>>(                                               \
-        P, ph.fdev, V, p->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->samples.p,                           \
-        (const uint16_t *)p->starts[0].p, (const uint8_t *)p->lams[0].p, (unsigned long long *)p->desc.p,           \
-        (FastCtl *)p->ctl.p, d_out, out_cap, ph.v3_stage, warp_bytes)
+        P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,                           \
+        (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p, (unsigned long long *)p->c->desc.p,           \
+        (FastCtl *)p->c->ctl.p, d_out, out_cap, (unsigned long long)p->emit_out_off, ph.v3_stage, warp_bytes)
     if (V.log == 7) { if (NL > 1) V3_LAUNCH(7, true); else V3_LAUNCH(7, false); }
     else { if (NL > 1) V3_LAUNCH(5, true); else V3_LAUNCH(5, false); }
 #undef V3_LAUNCH
     p->launches++;
     if (p->timing) CK(cudaEventRecord(p->ev[5], st));
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(p->ctl_host, p->ctl.p, sizeof(FastCtl), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p->c->ctl_host, p->c->ctl.p, sizeof(FastCtl), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (p->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
-    const size_t total = (size_t)p->ctl_host->total_out;
+    if (p->c->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
+    const size_t total = (size_t)p->c->ctl_host->total_out;
     *out_len = total;
-    if (p->ctl_host->overflow || total > out_cap) return KEX_ERR_OUT_CAP;
+    if (p->c->ctl_host->overflow || total + p->emit_out_off > out_cap) return KEX_ERR_OUT_CAP;
     // size the staging windows for the next run from the observed out/in ratio
     const double per_tile = (double)total / (double)ntiles;
     uint32_t want = (uint32_t)(per_tile * 1.25) + 256;
@@ -1452,24 +1474,24 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
   const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
   if (p->timing) CK(cudaEventRecord(p->ev[4], st));
   if (NL > 1)
-    k_emit_fast<true><<<grid, EF_NT, smem, st>>>(P, ph.fdev, p->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->samples.p,
-                                                 (const uint16_t *)p->starts[0].p, (const uint8_t *)p->lams[0].p,
-                                                 (unsigned long long *)p->desc.p, (FastCtl *)p->ctl.p, d_out, out_cap,
+    k_emit_fast<true><<<grid, EF_NT, smem, st>>>(P, ph.fdev, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,
+                                                 (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,
+                                                 (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,
                                                  ph.stage_bytes);
   else
-    k_emit_fast<false><<<grid, EF_NT, smem, st>>>(P, ph.fdev, p->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->samples.p,
-                                                  (const uint16_t *)p->starts[0].p, (const uint8_t *)p->lams[0].p,
-                                                  (unsigned long long *)p->desc.p, (FastCtl *)p->ctl.p, d_out, out_cap,
+    k_emit_fast<false><<<grid, EF_NT, smem, st>>>(P, ph.fdev, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,
+                                                  (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,
+                                                  (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,
                                                   ph.stage_bytes);
   p->launches++;
   if (p->timing) CK(cudaEventRecord(p->ev[5], st));
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(p->ctl_host, p->ctl.p, sizeof(FastCtl), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(p->c->ctl_host, p->c->ctl.p, sizeof(FastCtl), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (p->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
-  const size_t total = (size_t)p->ctl_host->total_out;
+  if (p->c->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
+  const size_t total = (size_t)p->c->ctl_host->total_out;
   *out_len = total;
-  if (p->ctl_host->overflow || total > out_cap) return KEX_ERR_OUT_CAP;
+  if (p->c->ctl_host->overflow || total > out_cap) return KEX_ERR_OUT_CAP;
   // size the staging window for the next run from the observed out/in ratio
   const double per_tile = (double)total / (double)ntiles;
   uint32_t want = (uint32_t)(per_tile * 1.25) + 512;
@@ -1489,13 +1511,13 @@ extern "C" int kex_shard_summarize(kex_program *p, const uint8_t *d_in, size_t n
   p->launches = 0;
   const uint32_t Q1 = p->phases[0].dev.Q + 1;
   if (n == 0) {
-    p->sh_in = d_in; p->sh_n = 0; p->sh_nchunks = 0; p->sh_phase = 0;
+    p->c->sh_in = d_in; p->c->sh_n = 0; p->c->sh_nchunks = 0; p->c->sh_phase = 0;
     for (uint32_t q = 0; q < Q1; ++q) h_state_map[q] = (uint16_t)q;
     return KEX_OK;
   }
   int rc = do_summarize(p, 0, d_in, n, st);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h_state_map, p->maps[p->nlevels - 1].p, Q1 * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_state_map, p->c->maps[p->c->nlevels - 1].p, Q1 * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return KEX_OK;
 }
@@ -1506,26 +1528,26 @@ extern "C" size_t kex_seam_bytes(const kex_program *p) {
   return ph.fast ? ph.fdev.NL : ph.dev.R;
 }
 
-extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *end_state, size_t *fail_pos,
-                              uint8_t *h_seam, void *stream) {
-  if (!p || !end_state || !fail_pos || !h_seam) return KEX_ERR_ARG;
-  CK(cudaSetDevice(p->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  PhaseHost &ph = p->phases[p->sh_phase];
+// Walk the summarized shard from its true start state: end state, first failing
+// position, and the shard's seam summary (how the seam code at its end maps to
+// its start).
+static int shard_walk_seam(kex_program *p, uint32_t start_state, uint32_t *end_state, size_t *fail_pos, uint8_t *h_seam,
+                           cudaStream_t st) {
+  PhaseHost &ph = p->phases[p->c->sh_phase];
   const PhaseDev &P = ph.dev;
   if (start_state > P.Q) return KEX_ERR_ARG;
   const uint32_t nseam = ph.fast ? ph.fdev.NL : P.R;
-  if (p->sh_n == 0) {
+  if (p->c->sh_n == 0) {
     *end_state = start_state; *fail_pos = (size_t)-1;
     for (uint32_t r = 0; r < nseam; ++r) h_seam[r] = (uint8_t)r;
     return KEX_OK;
   }
   int rc = do_walk(p, start_state, st);
   if (rc) return rc;
-  const unsigned long long f = p->res_host->fail_pos;
+  const unsigned long long f = p->c->res_host->fail_pos;
   *fail_pos = (f == KEX_NONE64) ? (size_t)-1 : (size_t)f;
-  *end_state = p->res_host->end_state;
-  const size_t n_eff = (f == KEX_NONE64) ? p->sh_n : (size_t)f;
+  *end_state = p->c->res_host->end_state;
+  const size_t n_eff = (f == KEX_NONE64) ? p->c->sh_n : (size_t)f;
   const size_t unit = ph.fast ? ph.tile() : (size_t)KEX_CHUNK;
   const size_t nchunks_eff = (n_eff + unit - 1) / unit;
   if (!ph.fast) return do_fate_up(p, nchunks_eff, h_seam, st);
@@ -1536,9 +1558,16 @@ extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *en
   size_t cnt[8];
   int nl = 0;
   if ((rc = lam_up(p, nchunks_eff, cnt, &nl, st))) return rc;
-  CK(cudaMemcpyAsync(h_seam, p->bmaps[nl - 1].p, nseam, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_seam, p->c->bmaps[nl - 1].p, nseam, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return KEX_OK;
+}
+
+extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *end_state, size_t *fail_pos,
+                              uint8_t *h_seam, void *stream) {
+  if (!p || !end_state || !fail_pos || !h_seam) return KEX_ERR_ARG;
+  CK(cudaSetDevice(p->device));
+  return shard_walk_seam(p, start_state, end_state, fail_pos, h_seam, (cudaStream_t)stream);
 }
 
 // Seam codes at the end of every shard from the shards' seam summaries (in
@@ -1568,7 +1597,7 @@ extern "C" int kex_stitch_live(const kex_program *p, const uint8_t *seams, size_
 
 extern "C" int kex_shard_emit(kex_program *p, uint32_t live_end_mask, size_t n_eff, uint8_t *d_out, size_t out_cap,
                               size_t *out_len, void *stream) {
-  if (!p || !out_len || n_eff > p->sh_n) return KEX_ERR_ARG;
+  if (!p || !out_len || n_eff > p->c->sh_n) return KEX_ERR_ARG;
   CK(cudaSetDevice(p->device));
   return do_emit(p, live_end_mask, n_eff, d_out, out_cap, out_len, (cudaStream_t)stream);
 }
@@ -1578,7 +1607,7 @@ static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t
                      size_t *out_len, int *status, size_t *fail_count, cudaStream_t st) {
   PhaseHost &ph = p->phases[phase];
   const PhaseDev &P = ph.dev;
-  p->sh_phase = phase;
+  p->c->sh_phase = phase;
   uint32_t end_state = P.init;
   size_t n_eff = n;
   bool failed = false;
@@ -1586,11 +1615,11 @@ static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t
     int rc = do_summarize(p, phase, d_in, n, st);
     if (rc) return rc;
     if ((rc = do_walk(p, P.init, st))) return rc;
-    const unsigned long long f = p->res_host->fail_pos;
+    const unsigned long long f = p->c->res_host->fail_pos;
     if (f != KEX_NONE64) { failed = true; n_eff = (size_t)f; }
-    end_state = p->res_host->end_state;
+    end_state = p->c->res_host->end_state;
   } else {
-    p->sh_in = d_in; p->sh_n = 0; p->sh_nchunks = 0;
+    p->c->sh_in = d_in; p->c->sh_n = 0; p->c->sh_nchunks = 0;
   }
   const int32_t fa = failed ? -1 : ph.fin[end_state];
   const bool accept = fa >= 0;
@@ -1667,7 +1696,7 @@ extern "C" int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n, uin
   if (p->timing) {
     CK(cudaEventRecord(p->ev[7], st));
     CK(cudaStreamSynchronize(st));
-    if (p->sh_n) {
+    if (p->c->sh_n) {
       cudaEventElapsedTime(&p->ms[0], p->ev[0], p->ev[1]);
       cudaEventElapsedTime(&p->ms[1], p->ev[2], p->ev[3]);
       if (*out_len) cudaEventElapsedTime(&p->ms[2], p->ev[4], p->ev[5]);
@@ -1678,6 +1707,139 @@ extern "C" int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n, uin
   return KEX_OK;
 }
 
+// Host pipeline for single-phase programs on the v3 kernels: the input is cut
+// into sub-waves that are copied in, evaluated as consecutive shards of one run
+// (state map -> true start state -> seam summary -> emit, exactly the sharded
+// entry points above) and copied out on three streams, so that the host<->device
+// copies of neighbouring sub-waves overlap the kernels and each other.  A
+// sub-wave is emitted as soon as the seam summary of its successor fixes the
+// seam code at its end; if a summary is not a constant map the pipeline gives up
+// and the whole input is evaluated at once.  Returns 1 when it gave up.
+static int run_host_pipelined(kex_program *p, const uint8_t *h_in, size_t n, uint8_t *h_out, size_t out_cap,
+                              size_t *out_len, int *status, size_t *fail_count, size_t wave) {
+  PhaseHost &ph = p->phases[0];
+  const uint32_t Q1 = ph.dev.Q + 1, NL = ph.fdev.NL;
+  if (!p->s_comp) {
+    CK(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+  }
+  const size_t nw = (n + wave - 1) / wave;
+  while (p->pipe_ev.size() < 2 * nw) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->pipe_ev.push_back(e);
+  }
+  uint8_t *d_in = (uint8_t *)p->hostio_in.p, *d_out = (uint8_t *)p->hostio_out.p;
+  for (size_t i = 0; i < nw; ++i) {
+    const size_t off = i * wave, len = (n - off < wave) ? (n - off) : wave;
+    CK(cudaMemcpyAsync(d_in + off, h_in + off, len, cudaMemcpyHostToDevice, p->s_h2d));
+    CK(cudaEventRecord(p->pipe_ev[2 * i], p->s_h2d));
+  }
+  cudaStream_t st = p->s_comp;
+  std::vector<uint16_t> map(Q1);
+  std::vector<uint8_t> seam(NL), seam_prev(NL);
+  uint32_t state = ph.dev.init;
+  size_t out_off = 0, n_fail = (size_t)-1;
+  long pending = -1;                    // sub-wave walked but not yet emitted
+  size_t pending_neff = 0;
+  int rc = KEX_OK;
+  bool gave_up = false, failed = false;
+  uint32_t launches = 0;
+  auto emit_one = [&](size_t k, uint32_t code, size_t n_eff) -> int {
+    p->c = &p->cx[k & 1];
+    p->emit_out_off = out_off;
+    size_t ol = 0;
+    p->launches = 0;
+    int r = do_emit(p, code, n_eff, d_out, out_cap, &ol, st);
+    launches += p->launches;
+    p->emit_out_off = 0;
+    if (r) return r;
+    if (ol) {
+      if (cudaEventRecord(p->pipe_ev[2 * k + 1], st) != cudaSuccess) return KEX_ERR_CUDA;
+      if (cudaStreamWaitEvent(p->s_d2h, p->pipe_ev[2 * k + 1], 0) != cudaSuccess) return KEX_ERR_CUDA;
+      if (cudaMemcpyAsync(h_out + out_off, d_out + out_off, ol, cudaMemcpyDeviceToHost, p->s_d2h) != cudaSuccess)
+        return KEX_ERR_CUDA;
+    }
+    out_off += ol;
+    return KEX_OK;
+  };
+  for (size_t i = 0; i < nw && rc == KEX_OK && !gave_up && !failed; ++i) {
+    const size_t off = i * wave, len = (n - off < wave) ? (n - off) : wave;
+    p->c = &p->cx[i & 1];
+    CK(cudaStreamWaitEvent(st, p->pipe_ev[2 * i], 0));
+    p->launches = 0;
+    if ((rc = do_summarize(p, 0, d_in + off, len, st))) break;
+    CK(cudaMemcpyAsync(map.data(), p->c->maps[p->c->nlevels - 1].p, Q1 * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t end_state = 0;
+    size_t fpos = (size_t)-1;
+    if ((rc = shard_walk_seam(p, state, &end_state, &fpos, seam.data(), st))) break;
+    launches += p->launches;
+    size_t n_eff = len;
+    if (fpos != (size_t)-1) { failed = true; n_eff = fpos; n_fail = off + fpos; }
+    if (pending >= 0) {
+      // seam code at the end of the pending sub-wave: this sub-wave's summary must be a constant map,
+      // or the run ends here (failure: nothing is live any more)
+      bool constant = true;
+      for (uint32_t l = 1; l < NL; ++l) constant = constant && seam[l] == seam[0];
+      if (!constant && !failed) { gave_up = true; break; }
+      const uint32_t code = failed ? seam[0] : seam[0];
+      if ((rc = emit_one((size_t)pending, code, pending_neff))) break;
+      pending = -1;
+    }
+    pending = (long)i;
+    pending_neff = n_eff;
+    state = end_state;
+    (void)map;
+  }
+  if (rc == KEX_OK && !gave_up && pending >= 0) {
+    // the last sub-wave: the end-of-input action (or the failure) fixes its seam code
+    p->c = &p->cx[pending & 1];
+    const int32_t fa = failed ? -1 : ph.fin[state];
+    const bool accept = fa >= 0;
+    const uint32_t code = accept ? final_code(ph, state) : 0u;
+    rc = emit_one((size_t)pending, code, pending_neff);
+    if (rc == KEX_OK) {
+      if (accept) {
+        const ActHdr &h = ph.acts[fa];
+        size_t tail = 0;
+        for (uint32_t k = 0; k < h.npieces; ++k) tail += ph.pieces[h.piece_off + k].len;
+        if (out_off + tail > out_cap) {
+          rc = KEX_ERR_OUT_CAP;
+          *out_len = out_off + tail;
+        } else {
+          size_t o = out_off;
+          for (uint32_t k = 0; k < h.npieces; ++k) {
+            const Piece &pc = ph.pieces[h.piece_off + k];
+            k_copy_tail<<<1, 64, 0, st>>>(ph.dev.consts + pc.off, pc.len, d_out + o);
+            launches++;
+            o += pc.len;
+          }
+          if (tail) {
+            CK(cudaStreamSynchronize(st));
+            CK(cudaMemcpyAsync(h_out + out_off, d_out + out_off, tail, cudaMemcpyDeviceToHost, p->s_d2h));
+          }
+          *out_len = o;
+          *status = KEX_ACCEPT;
+          *fail_count = 0;
+        }
+      } else {
+        *out_len = out_off / 16384 * 16384;   // whole 16 KiB flushes only (crt.c:140-159, 217-227)
+        *status = KEX_REJECT;
+        *fail_count = failed ? n_fail : n;
+      }
+    }
+  }
+  p->c = &p->cx[0];
+  cudaStreamSynchronize(p->s_h2d);
+  cudaStreamSynchronize(st);
+  cudaStreamSynchronize(p->s_d2h);
+  p->launches = launches;
+  if (gave_up) return 1;
+  return rc;
+}
+
 extern "C" int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n, uint8_t *h_out, size_t out_cap,
                             size_t *out_len, int *status, size_t *fail_count) {
   if (!p || !out_len || !status || !fail_count || (n && !h_in)) return KEX_ERR_ARG;
@@ -1685,6 +1847,18 @@ extern "C" int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n, uint8
   int rc;
   if ((rc = ensure(p, p->hostio_in, n + 16))) return rc;
   if ((rc = ensure(p, p->hostio_out, out_cap + 16))) return rc;
+  size_t wave = 128u << 20;
+  if (const char *e = getenv("KEX_HOST_WAVE_MIB")) { const long x = atol(e); if (x > 0) wave = (size_t)x << 20; }
+  if (p->phases.size() == 1 && p->phases[0].v3.ok && n >= 2 * wave && !getenv("KEX_NO_HOST_PIPELINE")) {
+    rc = run_host_pipelined(p, h_in, n, h_out, out_cap, out_len, status, fail_count, wave);
+    if (rc <= 0 && rc != KEX_ERR_OUT_CAP) return rc;
+    // the pipeline gave up (or the output did not fit): evaluate the resident input at once
+    rc = kex_run_device(p, (const uint8_t *)p->hostio_in.p, n, (uint8_t *)p->hostio_out.p, out_cap, out_len, status,
+                        fail_count, nullptr);
+    if (rc) return rc;
+    if (*out_len) CK(cudaMemcpy(h_out, p->hostio_out.p, *out_len, cudaMemcpyDeviceToHost));
+    return KEX_OK;
+  }
   if (n) CK(cudaMemcpy(p->hostio_in.p, h_in, n, cudaMemcpyHostToDevice));
   rc = kex_run_device(p, (const uint8_t *)p->hostio_in.p, n, (uint8_t *)p->hostio_out.p, out_cap, out_len, status,
                       fail_count, nullptr);

@@ -134,6 +134,26 @@ def test_vs_reference_binary(name):
     assert hashlib.sha256(out).hexdigest() == hashlib.sha256(r.stdout).hexdigest()
 
 
+@pytest.mark.parametrize("name", PROGS)
+def test_host_pipeline(name, monkeypatch):
+    """kex_run_host cuts large inputs into sub-waves that are copied, evaluated
+    as consecutive shards and copied back on three streams; with 1 MiB sub-waves
+    a 5 MiB input exercises every seam (accept, reject in the first / a middle /
+    the last sub-wave, output capacity error)."""
+    from kleenexlang_b200.runtime import KexError
+    prog, ssts = gpu_prog(program_source(name))
+    monkeypatch.setenv("KEX_HOST_WAVE_MIB", "1")
+    d = workloads.GENERATORS[name](5 << 20, seed=41).tobytes()
+    _check(prog, ssts, d)
+    for pos in (5, (1 << 20) - 1, 1 << 20, (2 << 20) + 12345, len(d) - 2):
+        _check(prog, ssts, d[:pos] + b"\x01" + d[pos + 1:])
+    with pytest.raises(KexError) as ei:
+        prog.run(d, out_cap=len(d) // 2)
+    assert ei.value.code == -3
+    monkeypatch.setenv("KEX_NO_HOST_PIPELINE", "1")
+    _check(prog, ssts, d)
+
+
 def test_pipeline_program():
     src = 'start: p >> a >> b\np := ~/abc/ "a"\na := /./ "b"\nb := /ab/ "c"\n   | ~/[^ab]/ "lol"\n'
     prog, ssts = gpu_prog(src)
