@@ -268,6 +268,12 @@ k3_seams(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n, size_t
 // ------------------------------------------------------------------ k3_emit
 extern __shared__ __align__(1024) uint8_t smem_v3[];
 
+// Staging windows are addressed through this swizzle: address bits 7-11 (the
+// 128-byte row) are XORed into bits 2-6 (the bank), so that lanes whose outputs
+// lie a multiple of 64 bytes apart -- the usual case, a lane's 32 input bytes
+// become about 64 output bytes -- hit different banks.  Words stay intact.
+__device__ __forceinline__ uint32_t swz(uint32_t a) { return a ^ ((a >> 5) & 0x7Cu); }
+
 // put byte 0 of e into byte k of acc
 __device__ __forceinline__ uint32_t put_byte0(uint32_t acc, uint32_t e, int k) {
   const uint32_t sel = k == 0 ? 0x3214u : k == 1 ? 0x3240u : k == 2 ? 0x3410u : 0x4210u;
@@ -327,7 +333,7 @@ __device__ __forceinline__ void v3_wstep(uint32_t pbe, uint32_t &EL, uint32_t ap
   EL = lds_u32(addr);
   o = sub_byte0(EL, o);
   const uint32_t b = k == 0 ? w : byte_prmt(w, k);
-  if (EL & 0x10000u) sts_u8(o, b);
+  if (EL & 0x10000u) sts_u8(swz(o), b);
   if (EL & 0x8000u) {
     // staging address (18 bits) | entry address / 4 << 18; the input byte, for a template with a hole
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(recp), "r"(o + (addr << 16)), "r"(b) : "memory");
@@ -359,19 +365,19 @@ __device__ __forceinline__ void v3_copy_template(uint32_t pool_abs, uint32_t poo
   const uint32_t ps = pool_abs + src;
 #pragma unroll
   for (uint32_t k = 0; k < 3; ++k)
-    if (k < head) sts_u8(o + k, lds_u8(ps + k));
+    if (k < head) sts_u8(swz(o + k), lds_u8(ps + k));
   const uint32_t x = src + head;                       // pool offset of the first whole word
   const uint32_t wsrc = pool_abs + (x & 3u) * pool_stride + (x & ~3u);
   const uint32_t wdst = o + head;
 #pragma unroll
   for (uint32_t i = 0; i < 6; ++i)
-    if (i < nw) sts_u32(wdst + 4u * i, lds_u32(wsrc + 4u * i));
-  for (uint32_t i = 6; i < nw; ++i) sts_u32(wdst + 4u * i, lds_u32(wsrc + 4u * i));
+    if (i < nw) sts_u32(swz(wdst + 4u * i), lds_u32(wsrc + 4u * i));
+  for (uint32_t i = 6; i < nw; ++i) sts_u32(swz(wdst + 4u * i), lds_u32(wsrc + 4u * i));
   const uint32_t tb = head + 4u * nw;
 #pragma unroll
   for (uint32_t k = 0; k < 3; ++k)
-    if (k < tail) sts_u8(o + tb + k, lds_u8(ps + tb + k));
-  if (t >> 24) sts_u8(o + (t >> 24) - 1u, byte);       // the hole takes the input byte
+    if (k < tail) sts_u8(swz(o + tb + k), lds_u8(ps + tb + k));
+  if (t >> 24) sts_u8(swz(o + (t >> 24) - 1u), byte);  // the hole takes the input byte
 }
 
 template <int LOG, bool REGS>
@@ -390,15 +396,25 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
   // ---- tables (once per CTA)
   const uint32_t mulB_abs = base + V.o_mulB, trans_abs = base + V.o_trans, be_abs = base + V.o_BE;
   if ((mulB_abs & 255u) || ((base + V.o_cls) & 255u) || be_abs + V.NE * STRIDE > 65536u) __trap();
-  for (uint32_t i = tid; i < NB * NG; i += blockDim.x) {
-    const uint32_t r = i / NG, g = i - r * NG;
-    *(uint16_t *)(smem_v3 + V.o_mulB + r * 256u + 2u * g) = (uint16_t)(mulB_abs + (uint32_t)F.mulB[i] * 256u);
+  // A row of the backward-element table is 256 bytes and holds `mcopies` copies of
+  // its NG entries, (1 << mshift) bytes apart; lane l uses copy l % mcopies (the
+  // copy offset is baked into byte 1 of its transition entries), so lanes in
+  // different rows rarely meet in a bank.
+  uint32_t mshift = 1;
+  while ((1u << mshift) < 2u * NG) ++mshift;
+  uint32_t mcopies = 128u >> mshift;            // the copies of a row span the 32 banks once
+  if (mcopies > REP) mcopies = REP;
+  if (mcopies < 1u) mcopies = 1u;
+  for (uint32_t i = tid; i < NB * NG * mcopies; i += blockDim.x) {
+    const uint32_t k = i % mcopies, j = i / mcopies, r = j / NG, g = j - r * NG;
+    *(uint16_t *)(smem_v3 + V.o_mulB + r * 256u + (k << mshift) + 2u * g) = (uint16_t)(mulB_abs + (uint32_t)F.mulB[j] * 256u);
   }
   for (uint32_t i = tid; i < Q1 * C * REP; i += blockDim.x) {
     const uint32_t ent = i / REP, s = i - ent * REP;
     const uint32_t e = F.trans2[ent];
     const uint32_t row = trans_abs + (e & 0xFFFFu) * C * STRIDE + s * 4u;
-    *(uint32_t *)(smem_v3 + V.o_trans + ent * STRIDE + s * 4u) = (row << 16) | ((e >> 16) & 0xFFu) | ((e >> 24) << 9);
+    const uint32_t gb = 2u * (e >> 24) + ((s % mcopies) << mshift);
+    *(uint32_t *)(smem_v3 + V.o_trans + ent * STRIDE + s * 4u) = (row << 16) | ((e >> 16) & 0xFFu) | (gb << 8);
   }
   for (uint32_t i = tid; i < V.NE * REP; i += blockDim.x) {
     const uint32_t ent = i / REP, s = i - ent * REP;
@@ -418,7 +434,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
   const uint32_t pbe = be_abs + slot4;
   const uint32_t wreg = V.o_warp + warp * warp_bytes;            // this warp's staging window, then its records
   const uint32_t stage_abs = base + wreg;
-  const uint32_t recs_abs = stage_abs + stage_bytes + 32u;
+  const uint32_t recs_abs = stage_abs + stage_bytes + 128u;    // window + one row of slack, both multiples of 128 (swizzle)
   const uint8_t *compB = smem_v3 + V.o_compB, *applyB = smem_v3 + V.o_applyB;
   // A group is the nwork consecutive tiles the worker warps of one CTA process
   // at a time.  The last warp of the CTA is the scan warp: it collects the tile
@@ -606,38 +622,24 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
         uint8_t *gal = out + (gbase - a);
         const uint32_t end = a + total;                             // in destination-chunk coordinates
         const uint32_t c_lo = a ? 1u : 0u, c_hi = end >> 4;         // whole chunks [c_lo, c_hi)
-        const uint32_t m = (16u - a) & 15u, rw = m >> 2, sh = (m & 3u) * 8u;
+        const uint32_t sh = ((0u - a) & 3u) * 8u;
         for (uint32_t c = c_lo + lane; c < c_hi; c += 32u) {
-          // source bytes start at 16c - a = 16(c - c_lo) + m  (relative to the window)
-          const uint32_t sa = stage_abs + 16u * (c - c_lo);
-          uint32_t W[8];
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(W[0]), "=r"(W[1]), "=r"(W[2]), "=r"(W[3]) : "r"(sa) : "memory");
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(W[4]), "=r"(W[5]), "=r"(W[6]), "=r"(W[7]) : "r"(sa + 16u) : "memory");
-          uint4 r4;
-          if (rw == 0) {
-            r4 = make_uint4(__funnelshift_r(W[0], W[1], sh), __funnelshift_r(W[1], W[2], sh),
-                            __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh));
-          } else if (rw == 1) {
-            r4 = make_uint4(__funnelshift_r(W[1], W[2], sh), __funnelshift_r(W[2], W[3], sh),
-                            __funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh));
-          } else if (rw == 2) {
-            r4 = make_uint4(__funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh),
-                            __funnelshift_r(W[4], W[5], sh), __funnelshift_r(W[5], W[6], sh));
-          } else {
-            r4 = make_uint4(__funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh),
-                            __funnelshift_r(W[5], W[6], sh), __funnelshift_r(W[6], W[7], sh));
-          }
-          *(uint4 *)(gal + 16u * c) = r4;
+          // source bytes start at window offset 16c - a: five words, funnel-shifted
+          const uint32_t sa = stage_abs + ((16u * c - a) & ~3u);
+          uint32_t W[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) W[k] = lds_u32_v(swz(sa + 4u * k));
+          *(uint4 *)(gal + 16u * c) = make_uint4(__funnelshift_r(W[0], W[1], sh), __funnelshift_r(W[1], W[2], sh),
+                                                 __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh));
         }
         // head (destination bytes a..15 of chunk 0) and tail (after the last whole chunk)
-        const uint8_t *stg = smem_v3 + wreg;
         if (a) {
           const uint32_t he = (end < 16u) ? end : 16u;
-          for (uint32_t b2 = a + lane; b2 < he; b2 += 32u) gal[b2] = stg[b2 - a];
+          for (uint32_t b2 = a + lane; b2 < he; b2 += 32u) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
         }
         if (c_hi >= c_lo) {
           for (uint32_t b2 = (c_hi << 4) + lane; b2 < end; b2 += 32u)
-            if (b2 >= a) gal[b2] = stg[b2 - a];
+            if (b2 >= a) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
         }
       }
       __syncwarp();

@@ -768,7 +768,7 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
   v.o_slots = sp; sp += 256u + 512u;
   sp = (sp + 127u) & ~127u;
   v.o_warp = sp;
-  if (sp + 4u * (2048u + 32u + V3_RECCAP * 8u) > 227u * 1024u) return KEX_OK;
+  if (sp + 4u * (2048u + 128u + V3_RECCAP * 8u) > 227u * 1024u) return KEX_OK;
   // forward table: two bytes per lookup when the pair table fits 16-bit row offsets
   const bool pair = (size_t)NM * C * C * 2 <= 65534 && (C - 1) * C * 2 <= 255;
   const uint32_t rowlen = pair ? C * C : C;
@@ -1414,7 +1414,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     // staging windows leave room for); every CTA must be resident because groups
     // are assigned statically and chained in order
     const V3Dev &V = ph.v3;
-    const uint32_t warp_bytes = (ph.v3_stage + 32u + V3_RECCAP * 8u + 15u) & ~15u;
+    const uint32_t warp_bytes = (ph.v3_stage + 128u + V3_RECCAP * 8u + 127u) & ~127u;
     uint32_t nwork = (uint32_t)(((size_t)V3_SMEM_MAX - V.o_warp) / warp_bytes);
     if (nwork > 31u) nwork = 31u;
     if (const char *e = getenv("KEX_V3_WORKERS")) { const uint32_t x = (uint32_t)atoi(e); if (x >= 1 && x < nwork) nwork = x; }
@@ -1456,7 +1456,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     uint32_t want = (uint32_t)(per_tile * 1.25) + 256;
     want = (want + 255u) & ~255u;
     if (want < 2048u) want = 2048u;
-    const uint32_t stage_max = (uint32_t)(((V3_SMEM_MAX - V.o_warp) / 8u - 32u - V3_RECCAP * 8u) & ~255u);   // keep >= 8 warps
+    const uint32_t stage_max = (uint32_t)(((V3_SMEM_MAX - V.o_warp) / 8u - 128u - V3_RECCAP * 8u) & ~255u);   // keep >= 8 warps
     if (want > stage_max) want = stage_max;
     if (want > ph.v3_stage || want + 1024u < ph.v3_stage) ph.v3_stage = want;
     return KEX_OK;
