@@ -37,7 +37,7 @@
 struct V3Dev {
   uint32_t ok;                 // phase runs on the v3 kernels
   uint32_t log;                // log2 of the table entry stride in bytes: 7 = one copy per lane, 5 = one per 8 lanes
-  uint32_t o_mulB, o_trans, o_BE, o_cls, o_compB, o_applyB, o_tpl2, o_pool, o_slots, o_warp;   // byte offsets in dynamic smem
+  uint32_t o_mulB, o_trans, o_BE, o_cls, o_compB, o_applyB, o_tpl2, o_pool, o_slots, o_guess, o_warp;   // byte offsets in dynamic smem
   uint32_t pool_stride;
   uint32_t NE;                 // NL * A emission entries
   const uint32_t *be3;         // [NE]  len | T << 15 | S << 16 | (lam_before * A) << 24;  S: emits exactly the input byte
@@ -380,6 +380,35 @@ __device__ __forceinline__ void v3_copy_template(uint32_t pool_abs, uint32_t poo
   if (t >> 24) sts_u8(swz(o + (t >> 24) - 1u), byte);  // the hole takes the input byte
 }
 
+// Staging window -> global with 16-byte stores aligned to the destination:
+// destination chunk c holds output bytes [16c - a, 16c - a + 16), a = gbase mod 16.
+__device__ __forceinline__ void v3_stage_out(uint32_t stage_abs, uint32_t total, unsigned long long gbase,
+                                             uint8_t *__restrict__ out, uint32_t lane) {
+  const uint32_t a = (uint32_t)(gbase & 15ull);
+  uint8_t *gal = out + (gbase - a);
+  const uint32_t end = a + total;                             // in destination-chunk coordinates
+  const uint32_t c_lo = a ? 1u : 0u, c_hi = end >> 4;         // whole chunks [c_lo, c_hi)
+  const uint32_t sh = ((0u - a) & 3u) * 8u;
+  for (uint32_t c = c_lo + lane; c < c_hi; c += 32u) {
+    // source bytes start at window offset 16c - a: five words, funnel-shifted
+    const uint32_t sa = stage_abs + ((16u * c - a) & ~3u);
+    uint32_t W[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) W[k] = lds_u32_v(swz(sa + 4u * k));
+    *(uint4 *)(gal + 16u * c) = make_uint4(__funnelshift_r(W[0], W[1], sh), __funnelshift_r(W[1], W[2], sh),
+                                           __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh));
+  }
+  // head (destination bytes a..15 of chunk 0) and tail (after the last whole chunk)
+  if (a) {
+    const uint32_t he = (end < 16u) ? end : 16u;
+    for (uint32_t b2 = a + lane; b2 < he; b2 += 32u) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
+  }
+  if (c_hi >= c_lo) {
+    for (uint32_t b2 = (c_hi << 4) + lane; b2 < end; b2 += 32u)
+      if (b2 >= a) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
+  }
+}
+
 template <int LOG, bool REGS>
 __global__ void __launch_bounds__(1024, 1)
 k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
@@ -421,6 +450,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
     *(uint32_t *)(smem_v3 + V.o_BE + ent * STRIDE + s * 4u) = V.be3[ent];
   }
   for (uint32_t i = tid; i < 256; i += blockDim.x) smem_v3[V.o_cls + i] = P.cls[i];
+  for (uint32_t i = tid; i < Q1; i += blockDim.x) smem_v3[V.o_guess + i] = 0xFFu;
   for (uint32_t i = tid; i < NB * NB; i += blockDim.x) smem_v3[V.o_compB + i] = F.compB[i];
   for (uint32_t i = tid; i < NB * NL; i += blockDim.x) smem_v3[V.o_applyB + i] = F.applyB[i];
   for (uint32_t i = tid; i < V.NE; i += blockDim.x) *(uint32_t *)(smem_v3 + V.o_tpl2 + 4u * i) = V.tpl2[i];
@@ -450,11 +480,13 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
   const uint32_t ngroups = (ntiles + nwork - 1u) / nwork;
   const uint32_t bar_n = blockDim.x;
   uint32_t par = 0;
+  const uint32_t guess_abs = base + V.o_guess;        // [Q+1] live set usually seen when a half ends in this state
+  uint32_t spec_ctr = 0;
 
   if (warp == nwork) {
     // =============================================================== scan warp
     for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x, par ^= 1u) {
-      asm volatile("bar.sync 1, %0;" ::"r"(bar_n) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1u + par), "r"(bar_n) : "memory");
       const uint32_t tv = (lane < nwork) ? slots[par * 32u + lane] : 0u;
       uint32_t inc_s = tv;
 #pragma unroll
@@ -507,12 +539,13 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       }
       bases[par * 32u + lane] = out_off + gex + (unsigned long long)(inc_s - tv);
       __threadfence_block();
-      asm volatile("bar.arrive 2, %0;" ::"r"(bar_n) : "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(3u + par), "r"(bar_n) : "memory");
     }
     return;
   }
 
   // ================================================================= workers
+  uint32_t prev_total = 0xFFFFFFFFu;                  // tile whose staging window has not left yet
   for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x, par ^= 1u) {
     const uint32_t tile = grp * nwork + warp;
     const bool active = tile < ntiles;
@@ -542,35 +575,77 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
     }
     const uint32_t lam_tile = (REGS && active) ? lam_end[tile] : 0u;
 
-    // ---- forward walk
+    // ---- forward walk, live set after each half, count.
+    // Exact: the forward walk also multiplies up the backward element of each
+    // half; a suffix composition over the warp gives the live set at every half's
+    // end.  Speculative (full tiles, programs with registers): the live set at a
+    // half's end is guessed from the state there (`guess`, learnt from exactly
+    // evaluated tiles), the forward walk skips the backward elements, and the
+    // count pass -- which walks the live sets backwards exactly -- must reproduce
+    // at every half's start the value assumed for the end of the half before it
+    // (by induction from the tile's known end value every guess was then right).
     uint32_t ap[8];
-    uint32_t EA = (trans_abs + sA * C * STRIDE + slot4) << 16, EB = (trans_abs + sB * C * STRIDE + slot4) << 16;
-    uint32_t MA = mulB_abs, MB = mulB_abs;
-    if (full) v3_forward<LOG, REGS, true>(cls_abs, w, cnt_pos, EA, EB, MA, MB, ap);
-    else v3_forward<LOG, REGS, false>(cls_abs, w, cnt_pos, EA, EB, MA, MB, ap);
-
-    // ---- live set after each half
-    uint32_t lamT = 0, lamH = 0;                     // after the thread's last byte / after half A
+    uint32_t ELA = 0, ELB = 0, accA = 0, accB = 0;
+    const uint32_t E0 = (trans_abs + sA * C * STRIDE + slot4) | ((trans_abs + sB * C * STRIDE + slot4) << 16);
+    bool spec = false;
+    uint32_t gix = 0;                                // guess slots of the two halves' end states
     if (REGS) {
-      const uint32_t mbA = (MA - mulB_abs) >> 8, mbB = (MB - mulB_abs) >> 8;
-      uint32_t x = compB[mbA * NB + mbB];            // this thread's element; suffix composition inside the warp
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_down_sync(0xFFFFFFFFu, x, d);
-        if (lane + d < 32u) x = compB[x * NB + y];
+      gix = sB | (__shfl_down_sync(0xFFFFFFFFu, sA, 1) << 16);
+      spec = full && (int)spec_ctr >= 0;
+      if (spec) {
+        const uint32_t gH = lds_u8_v(guess_abs + (gix & 0xFFFFu));
+        const uint32_t gT = (lane == 31u) ? lam_tile : lds_u8_v(guess_abs + (gix >> 16));
+        spec = __all_sync(0xFFFFFFFFu, gH != 0xFFu && gT != 0xFFu);
+        ELA = (gH * A) << 24;
+        ELB = (gT * A) << 24;
       }
-      uint32_t ex = __shfl_down_sync(0xFFFFFFFFu, x, 1);
-      if (lane == 31u) ex = 0;
-      lamT = applyB[ex * NL + lam_tile];
-      lamH = applyB[mbB * NL + lamT];
+      if (spec) {
+        uint32_t EA = E0 << 16, EB = E0 & 0xFFFF0000u, MA = 0, MB = 0;
+        v3_forward<LOG, false, true>(cls_abs, w, cnt_pos, EA, EB, MA, MB, ap);
+        uint32_t ea = ELA, eb = ELB;
+        v3_count<LOG>(pbe, ap, ea, eb, accA, accB);
+        // half B starts with what half A assumed at its end; the next lane's half A
+        // starts with what this lane's half B assumed at its end
+        const uint32_t nextA = __shfl_down_sync(0xFFFFFFFFu, ea, 1);
+        const bool good = ((eb ^ ELA) >> 24) == 0u && (lane == 31u || ((nextA ^ ELB) >> 24) == 0u);
+        spec = __all_sync(0xFFFFFFFFu, good);
+        if (!spec) spec_ctr += 0x10000u;             // a miss
+      }
     }
-
-    // ---- count
-    uint32_t ELA = (lamH * A) << 24, ELB = (lamT * A) << 24;
-    uint32_t accA = 0, accB = 0;
-    {
+    if (!spec) {
+      uint32_t EA = E0 << 16, EB = E0 & 0xFFFF0000u, MA = mulB_abs, MB = mulB_abs;
+      if (full) v3_forward<LOG, REGS, true>(cls_abs, w, cnt_pos, EA, EB, MA, MB, ap);
+      else v3_forward<LOG, REGS, false>(cls_abs, w, cnt_pos, EA, EB, MA, MB, ap);
+      uint32_t lamT = 0, lamH = 0;                   // live set after the thread's last byte / after half A
+      if (REGS) {
+        const uint32_t mbA = (MA - mulB_abs) >> 8, mbB = (MB - mulB_abs) >> 8;
+        uint32_t x = compB[mbA * NB + mbB];          // this thread's element; suffix composition inside the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_down_sync(0xFFFFFFFFu, x, d);
+          if (lane + d < 32u) x = compB[x * NB + y];
+        }
+        uint32_t ex = __shfl_down_sync(0xFFFFFFFFu, x, 1);
+        if (lane == 31u) ex = 0;
+        lamT = applyB[ex * NL + lam_tile];
+        lamH = applyB[mbB * NL + lamT];
+        if (full) {
+          // learn from an exactly evaluated tile
+          sts_u8(guess_abs + (gix & 0xFFFFu), lamH);
+          if (lane != 31u) sts_u8(guess_abs + (gix >> 16), lamT);
+        }
+      }
+      ELA = (lamH * A) << 24;
+      ELB = (lamT * A) << 24;
+      accA = 0;
+      accB = 0;
       uint32_t ea = ELA, eb = ELB;
       v3_count<LOG>(pbe, ap, ea, eb, accA, accB);
+    }
+    if (REGS) {
+      // tiles in the low half, misses in the high half; guessing stops (sign bit) when a quarter of the tiles miss
+      ++spec_ctr;
+      if ((spec_ctr & 0xFFFFu) == 64u) spec_ctr = ((spec_ctr >> 16) * 4u > 64u) ? 0x80000000u : 0u;
     }
     const uint32_t cntA = accA & 0x3FFFu, cntB = accB & 0x3FFFu, nrA = accA >> 14, nrB = accB >> 14;
     const uint32_t v = (cntA + cntB) | ((nrA + nrB) << 20);
@@ -593,7 +668,20 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       }
     }
     __threadfence_block();
-    asm volatile("bar.arrive 1, %0;" ::"r"(bar_n) : "memory");
+    asm volatile("bar.arrive %0, %1;" ::"r"(1u + par), "r"(bar_n) : "memory");
+    // ---- the previous tile leaves its staging window only now: its global offset
+    // had this tile's load, forward walk and count pass to arrive
+    if (prev_total != 0xFFFFFFFFu) {
+      asm volatile("bar.sync %0, %1;" ::"r"(3u + (par ^ 1u)), "r"(bar_n) : "memory");
+      const unsigned long long gb = bases[(par ^ 1u) * 32u + warp];
+      if (gb + prev_total > (unsigned long long)out_cap) {
+        if (lane == 0) atomicExch(&ctl->overflow, 1u);
+      } else {
+        v3_stage_out(stage_abs, prev_total, gb, out, lane);
+      }
+      __syncwarp();
+      prev_total = 0xFFFFFFFFu;
+    }
     const uint32_t o_end = xs & 0xFFFFFu;                        // bytes up to and including this thread
     const uint32_t rec_excl = (xs >> 20) - (nrA + nrB);
     if (total + 16u <= stage_bytes && total_recs <= V3_RECCAP) {
@@ -610,44 +698,12 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
         v3_copy_template(pool_abs, V.pool_stride, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
       }
       __syncwarp();
-      // ---- global offset of this tile, then staging window -> global with
-      // 16-byte stores aligned to the destination: destination chunk c holds
-      // output bytes [16c - a, 16c - a + 16), a = offset mod 16
-      asm volatile("bar.sync 2, %0;" ::"r"(bar_n) : "memory");
-      const unsigned long long gbase = bases[par * 32u + warp];
-      if (gbase + total > (unsigned long long)out_cap) {
-        if (lane == 0) atomicExch(&ctl->overflow, 1u);
-      } else {
-        const uint32_t a = (uint32_t)(gbase & 15ull);
-        uint8_t *gal = out + (gbase - a);
-        const uint32_t end = a + total;                             // in destination-chunk coordinates
-        const uint32_t c_lo = a ? 1u : 0u, c_hi = end >> 4;         // whole chunks [c_lo, c_hi)
-        const uint32_t sh = ((0u - a) & 3u) * 8u;
-        for (uint32_t c = c_lo + lane; c < c_hi; c += 32u) {
-          // source bytes start at window offset 16c - a: five words, funnel-shifted
-          const uint32_t sa = stage_abs + ((16u * c - a) & ~3u);
-          uint32_t W[5];
-#pragma unroll
-          for (int k = 0; k < 5; ++k) W[k] = lds_u32_v(swz(sa + 4u * k));
-          *(uint4 *)(gal + 16u * c) = make_uint4(__funnelshift_r(W[0], W[1], sh), __funnelshift_r(W[1], W[2], sh),
-                                                 __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh));
-        }
-        // head (destination bytes a..15 of chunk 0) and tail (after the last whole chunk)
-        if (a) {
-          const uint32_t he = (end < 16u) ? end : 16u;
-          for (uint32_t b2 = a + lane; b2 < he; b2 += 32u) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
-        }
-        if (c_hi >= c_lo) {
-          for (uint32_t b2 = (c_hi << 4) + lane; b2 < end; b2 += 32u)
-            if (b2 >= a) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
-        }
-      }
-      __syncwarp();
+      prev_total = total;                                          // staged out after the next tile's count
     } else {
       // ---- the tile's output exceeds the staging window: byte stores to global.
       // Input words and action ids are parked in the (idle) staging window so
       // that the loop can stay rolled.
-      asm volatile("bar.sync 2, %0;" ::"r"(bar_n) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(3u + par), "r"(bar_n) : "memory");
       const unsigned long long gbase = bases[par * 32u + warp];
       if (gbase + total > (unsigned long long)out_cap) {
         if (lane == 0) atomicExch(&ctl->overflow, 1u);
@@ -672,6 +728,16 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
         }
       }
       __syncwarp();
+    }
+  }
+  if (prev_total != 0xFFFFFFFFu) {
+    // the last tile of this warp (par has advanced past its round)
+    asm volatile("bar.sync %0, %1;" ::"r"(3u + (par ^ 1u)), "r"(bar_n) : "memory");
+    const unsigned long long gb = bases[(par ^ 1u) * 32u + warp];
+    if (gb + prev_total > (unsigned long long)out_cap) {
+      if (lane == 0) atomicExch(&ctl->overflow, 1u);
+    } else {
+      v3_stage_out(stage_abs, prev_total, gb, out, lane);
     }
   }
 }

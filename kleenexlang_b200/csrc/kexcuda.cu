@@ -766,6 +766,7 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
   v.o_pool = sp; sp += 4u * v.pool_stride;
   sp = (sp + 15u) & ~15u;
   v.o_slots = sp; sp += 256u + 512u;
+  v.o_guess = sp; sp += (Q1 + 15u) & ~15u;
   sp = (sp + 127u) & ~127u;
   v.o_warp = sp;
   if (sp + 4u * (2048u + 128u + V3_RECCAP * 8u) > 227u * 1024u) return KEX_OK;
