@@ -23,10 +23,10 @@ GIB = float(1 << 30)
 PROGRAM = "csv2json"
 OUT_PER_IN = 1.954            # +127 B per ~133 B row
 ALGO_BYTES_PER_IN = 1.0 + OUT_PER_IN
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_emit launch from the
-# committed `ncu --set full` capture, per input byte of that launch (profiles/);
-# None until a capture has been read back.
-EMIT_TRAFFIC_PER_IN = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one k3_emit launch from the
+# committed `ncu --set full` capture (profiles/r01_ncu_v3_full_16gib.txt: 19.287 GB
+# read + 33.383 GB written for 17.180 GB of input), per input byte of that launch.
+EMIT_TRAFFIC_PER_IN = (19.286725 + 33.382569) / 17.179869
 
 
 def peaks():
@@ -346,10 +346,11 @@ def main():
             ach = ALGO_BYTES_PER_IN_measured(n, expect_out) / (emit_ms / 1000.0) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": (EMIT_TRAFFIC_PER_IN * n) if EMIT_TRAFFIC_PER_IN else None,
-                                "kernel": "k_emit_fast", "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % how,
+                                "kernel": "k3_emit" if info["chunk_bytes"] == 1024 else "k_emit_fast",
+                                "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % how,
                                 "algorithmic_bytes_per_launch": n + expect_out,
-                                "kernel_ms": {"k_fwd_monoid": kms[0] / args.steps, "k_seams": kms[1] / args.steps,
-                                              "k_emit_fast": emit_ms, "all_device_work": kms[3] / args.steps},
+                                "kernel_ms": {"forward_monoid": kms[0] / args.steps, "seams": kms[1] / args.steps,
+                                              "emit": emit_ms, "all_device_work": kms[3] / args.steps},
                                 "pipeline_frac": (n + expect_out) / (ms_per_step / 1000.0) / 1e9 / peak}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
