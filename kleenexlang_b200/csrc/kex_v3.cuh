@@ -48,6 +48,8 @@ struct V3Dev {
   uint32_t recip;              // row offset -> element id: __umulhi(off, recip)
   uint32_t fwd_entries;
   const uint16_t *fwdtab;      // row byte offset of the product element
+  const uint16_t *compF;       // [NM][NM] element id of (first, then second)
+  uint32_t NM;
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -103,20 +105,18 @@ __device__ __forceinline__ void ld_stream32(const uint8_t *p, uint32_t (&r)[8]) 
   if (PAIR) { F3_PAIR(m, w, 0) F3_PAIR(m, w, 2) } else { F3_ONE(m, w, 0) F3_ONE(m, w, 1) F3_ONE(m, w, 2) F3_ONE(m, w, 3) }
 #define F3_16(m, v) F3_WORD(m, v.x) F3_WORD(m, v.y) F3_WORD(m, v.z) F3_WORD(m, v.w)
 
+// One warp per pair of 4 KiB chunks: lane l walks block l (128 bytes) of both
+// chunks (two independent chains), so every load instruction of the warp reads
+// inside one contiguous 4 KiB region.  Within a block the prefix element before
+// every 16 bytes is sampled relative to the block start; the blocks' elements
+// are composed across the warp (element composition table in L2) into the
+// prefix element before every block (`blockpre`) and the chunk's state map.
+//   state before sub-chunk j of chunk c = applyF[samples[c][j]][ applyF[blockpre[c][j / 8]][chunk start] ]
 template <bool PAIR>
-__device__ __forceinline__ void f3_finish(const PhaseDev &P, const FastDev &F, const V3Dev &V, uint32_t m,
-                                          uint16_t *__restrict__ row) {
-  const uint32_t Q1 = P.Q + 1;
-  const uint32_t id = __umulhi(m, V.recip);
-  const uint16_t *ap = F.applyF + (size_t)id * Q1;
-  for (uint32_t q = 0; q < Q1; ++q) row[q] = ap[q];
-}
-
-// one chunk of arbitrary length (the last one); rolled
-template <bool PAIR>
-__device__ void f3_chunk_tail(const PhaseDev &P, const FastDev &F, const V3Dev &V, const uint8_t *clsA,
-                              const uint8_t *clsB, const uint8_t *tab, const uint8_t *__restrict__ p, uint32_t len,
-                              uint16_t *__restrict__ srow, uint16_t *__restrict__ mrow) {
+__device__ __forceinline__ uint32_t f3_block_tail(const PhaseDev &P, const FastDev &F, const V3Dev &V,
+                                                  const uint8_t *clsA, const uint8_t *clsB, const uint8_t *tab,
+                                                  const uint8_t *__restrict__ p, uint32_t len,
+                                                  uint16_t *__restrict__ srow) {
   uint32_t m = 0;
   const uint32_t C = P.C;
   for (uint32_t j = 0; j < len;) {
@@ -126,7 +126,6 @@ __device__ void f3_chunk_tail(const PhaseDev &P, const FastDev &F, const V3Dev &
         m = *(const uint16_t *)(tab + m + clsA[p[j]] + clsB[p[j + 1]]);
         j += 2;
       } else {
-        // odd tail: one single step through the element table in global memory
         const uint32_t id = __umulhi(m, V.recip);
         m = (uint32_t)F.mulF[id * C + P.cls[p[j]]] * V.rowbytes;
         j += 1;
@@ -136,17 +135,31 @@ __device__ void f3_chunk_tail(const PhaseDev &P, const FastDev &F, const V3Dev &
       j += 1;
     }
   }
-  f3_finish<PAIR>(P, F, V, m, mrow);
+  return __umulhi(m, V.recip);
 }
+
+// inclusive composition over the warp: lane l gets e_0 . e_1 ... e_l (earlier first)
+__device__ __forceinline__ uint32_t f3_warp_compose(const uint16_t *__restrict__ compF, uint32_t NM, uint32_t e,
+                                                    uint32_t lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, e, d);
+    if (lane >= (uint32_t)d) e = __ldg(compF + (size_t)y * NM + e);
+  }
+  return e;
+}
+
+#define V3_BLK 128u                      // bytes per lane and chunk
+#define V3_BPC (KEX_CHUNK / V3_BLK)      // blocks per chunk (32 = one warp)
 
 template <bool PAIR>
 __global__ void __launch_bounds__(512, 2)
 k3_fwd(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n, size_t nchunks,
-       uint16_t *__restrict__ samples, uint16_t *__restrict__ maps) {
+       uint16_t *__restrict__ samples, uint16_t *__restrict__ blockpre, uint16_t *__restrict__ maps) {
   extern __shared__ __align__(16) uint8_t smem_f3[];
   uint8_t *clsA = smem_f3, *clsB = smem_f3 + 256;
   uint8_t *tab = smem_f3 + 512;
-  const uint32_t C = P.C, Q1 = P.Q + 1;
+  const uint32_t C = P.C, Q1 = P.Q + 1, NM = V.NM;
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
     const uint32_t c = P.cls[i];
     clsA[i] = (uint8_t)(PAIR ? c * C * 2u : c * 2u);
@@ -154,53 +167,62 @@ k3_fwd(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n,
   }
   for (uint32_t i = threadIdx.x; i < V.fwd_entries; i += blockDim.x) ((uint16_t *)tab)[i] = V.fwdtab[i];
   __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, wpc = blockDim.x >> 5;
   const size_t npairs = (nchunks + 1) / 2;
   const uint32_t recip = V.recip;
-  for (size_t pr = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs; pr += (size_t)gridDim.x * blockDim.x) {
+  const size_t gw = (size_t)blockIdx.x * wpc + (threadIdx.x >> 5), nw = (size_t)gridDim.x * wpc;
+  for (size_t pr = gw; pr < npairs; pr += nw) {
     const size_t c0 = 2 * pr, c1 = c0 + 1;
     const size_t base0 = c0 * KEX_CHUNK;
     const bool two = c1 < nchunks;
     const uint32_t len0 = (uint32_t)((n - base0 < KEX_CHUNK) ? (n - base0) : KEX_CHUNK);
     const uint32_t len1 = two ? (uint32_t)((n - base0 - KEX_CHUNK < KEX_CHUNK) ? (n - base0 - KEX_CHUNK) : KEX_CHUNK) : 0u;
+    uint16_t *sa = samples + c0 * V3_SPC + lane * (V3_BLK / V3_SUB), *sb = sa + V3_SPC;
+    uint32_t ea, eb;                         // element ids of this lane's two blocks
     if (len0 == KEX_CHUNK && len1 == KEX_CHUNK) {
-      // two independent chains; the next 32 bytes of each are in flight while the
-      // current ones are walked (one full 32-byte sector per load)
-      const uint8_t *pa = in + base0, *pb = pa + KEX_CHUNK;
-      uint16_t *sa = samples + c0 * V3_SPC, *sb = sa + V3_SPC;
+      const uint8_t *pa = in + base0 + lane * V3_BLK, *pb = pa + KEX_CHUNK;
       uint32_t ma = 0, mb = 0;
       uint32_t ca[8], cb[8], na[8], nb[8];
       ld_stream32(pa, ca);
       ld_stream32(pb, cb);
-      uint32_t pend_a = 0, pend_b = 0;
-#pragma unroll 2
-      for (uint32_t blk = 0; blk < KEX_CHUNK / 32u; ++blk) {
-        const uint32_t nx = (blk + 1u < KEX_CHUNK / 32u) ? (blk + 1u) * 32u : blk * 32u;
+      uint32_t qa[4], qb[4];
+#pragma unroll
+      for (uint32_t blk = 0; blk < V3_BLK / 32u; ++blk) {
+        const uint32_t nx = (blk + 1u < V3_BLK / 32u) ? (blk + 1u) * 32u : blk * 32u;
         ld_stream32(pa + nx, na);
         ld_stream32(pb + nx, nb);
-        uint32_t ia0 = ma, ib0 = mb;
+        const uint32_t ia0 = ma, ib0 = mb;
         F3_WORD(ma, ca[0]) F3_WORD(mb, cb[0]) F3_WORD(ma, ca[1]) F3_WORD(mb, cb[1])
         F3_WORD(ma, ca[2]) F3_WORD(mb, cb[2]) F3_WORD(ma, ca[3]) F3_WORD(mb, cb[3])
-        uint32_t ia1 = ma, ib1 = mb;
+        const uint32_t ia1 = ma, ib1 = mb;
         F3_WORD(ma, ca[4]) F3_WORD(mb, cb[4]) F3_WORD(ma, ca[5]) F3_WORD(mb, cb[5])
         F3_WORD(ma, ca[6]) F3_WORD(mb, cb[6]) F3_WORD(ma, ca[7]) F3_WORD(mb, cb[7])
-        const uint32_t qa = __umulhi(ia0, recip) | (__umulhi(ia1, recip) << 16);
-        const uint32_t qb = __umulhi(ib0, recip) | (__umulhi(ib1, recip) << 16);
-        if (blk & 1u) {
-          *(uint2 *)(sa + (blk - 1u) * 2u) = make_uint2(pend_a, qa);
-          *(uint2 *)(sb + (blk - 1u) * 2u) = make_uint2(pend_b, qb);
-        } else {
-          pend_a = qa;
-          pend_b = qb;
-        }
+        qa[blk] = __umulhi(ia0, recip) | (__umulhi(ia1, recip) << 16);
+        qb[blk] = __umulhi(ib0, recip) | (__umulhi(ib1, recip) << 16);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { ca[k] = na[k]; cb[k] = nb[k]; }
       }
-      f3_finish<PAIR>(P, F, V, ma, maps + c0 * Q1);
-      f3_finish<PAIR>(P, F, V, mb, maps + c1 * Q1);
+      *(uint4 *)sa = make_uint4(qa[0], qa[1], qa[2], qa[3]);
+      *(uint4 *)sb = make_uint4(qb[0], qb[1], qb[2], qb[3]);
+      ea = __umulhi(ma, recip);
+      eb = __umulhi(mb, recip);
     } else {
-      f3_chunk_tail<PAIR>(P, F, V, clsA, clsB, tab, in + base0, len0, samples + c0 * V3_SPC, maps + c0 * Q1);
-      if (two) f3_chunk_tail<PAIR>(P, F, V, clsA, clsB, tab, in + base0 + KEX_CHUNK, len1, samples + c1 * V3_SPC,
-                                   maps + c1 * Q1);
+      const uint32_t lo = lane * V3_BLK;
+      const uint32_t l0 = (lo < len0) ? ((len0 - lo < V3_BLK) ? (len0 - lo) : V3_BLK) : 0u;
+      const uint32_t l1 = (lo < len1) ? ((len1 - lo < V3_BLK) ? (len1 - lo) : V3_BLK) : 0u;
+      ea = f3_block_tail<PAIR>(P, F, V, clsA, clsB, tab, in + base0 + lo, l0, sa);
+      eb = f3_block_tail<PAIR>(P, F, V, clsA, clsB, tab, in + base0 + KEX_CHUNK + lo, l1, sb);
+    }
+    // prefix element before every block, element of the whole chunk
+    const uint32_t xa = f3_warp_compose(V.compF, NM, ea, lane), xb = f3_warp_compose(V.compF, NM, eb, lane);
+    uint32_t pa2 = __shfl_up_sync(0xFFFFFFFFu, xa, 1), pb2 = __shfl_up_sync(0xFFFFFFFFu, xb, 1);
+    if (lane == 0) { pa2 = 0; pb2 = 0; }
+    blockpre[c0 * V3_BPC + lane] = (uint16_t)pa2;
+    const uint32_t ta = __shfl_sync(0xFFFFFFFFu, xa, 31), tb = __shfl_sync(0xFFFFFFFFu, xb, 31);
+    for (uint32_t q = lane; q < Q1; q += 32u) maps[c0 * Q1 + q] = F.applyF[(size_t)ta * Q1 + q];
+    if (two) {
+      blockpre[c1 * V3_BPC + lane] = (uint16_t)pb2;
+      for (uint32_t q = lane; q < Q1; q += 32u) maps[c1 * Q1 + q] = F.applyF[(size_t)tb * Q1 + q];
     }
   }
 }
@@ -210,7 +232,7 @@ k3_fwd(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n,
 // mulB u8 [NB*NG], constB [NB].
 __global__ void __launch_bounds__(256)
 k3_seams(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n, size_t ntiles,
-         const uint16_t *__restrict__ samples, const uint16_t *__restrict__ chunk_start,
+         const uint16_t *__restrict__ blockpre, const uint16_t *__restrict__ chunk_start,
          const uint16_t *__restrict__ maps, uint8_t *__restrict__ bmaps, RunResult *__restrict__ res) {
   extern __shared__ __align__(16) uint8_t smem_s3[];
   const uint32_t Q = P.Q, Q1 = Q + 1, C = P.C, NL = F.NL, NG = F.NG, NB = F.NB;
@@ -229,9 +251,10 @@ k3_seams(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n, size_t
   const uint32_t cs = chunk_start[chunk];
   uint32_t s = Q, endst = Q;
   if (cs != Q) {
-    s = F.applyF[(size_t)samples[tile * V3_SPT] * Q1 + cs];
+    // a tile starts on a block boundary: its sample there is the identity
+    s = F.applyF[(size_t)blockpre[tile * (V3_TILE / V3_BLK)] * Q1 + cs];
     const bool last_in_chunk = ((tile + 1) % V3_TPC == 0) || (tile + 1 == ntiles);
-    endst = last_in_chunk ? maps[chunk * Q1 + cs] : F.applyF[(size_t)samples[(tile + 1) * V3_SPT] * Q1 + cs];
+    endst = last_in_chunk ? maps[chunk * Q1 + cs] : F.applyF[(size_t)blockpre[(tile + 1) * (V3_TILE / V3_BLK)] * Q1 + cs];
   }
   if (tile == ntiles - 1) res->end_state = endst;
   const bool failing = (s != Q) && (endst == Q);
@@ -412,9 +435,10 @@ __device__ __forceinline__ void v3_stage_out(uint32_t stage_abs, uint32_t total,
 template <int LOG, bool REGS>
 __global__ void __launch_bounds__(1024, 1)
 k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
-        const uint16_t *__restrict__ samples, const uint16_t *__restrict__ chunk_start,
-        const uint8_t *__restrict__ lam_end, unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl,
-        uint8_t *__restrict__ out, size_t out_cap, unsigned long long out_off, uint32_t stage_bytes,
+        const uint16_t *__restrict__ samples, const uint16_t *__restrict__ blockpre,
+        const uint16_t *__restrict__ chunk_start, const uint8_t *__restrict__ lam_end,
+        unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl, uint8_t *__restrict__ out, size_t out_cap,
+        unsigned long long out_off, uint32_t stage_bytes,
         uint32_t warp_bytes) {
   constexpr uint32_t STRIDE = 1u << LOG, REP = STRIDE / 4u;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarp = blockDim.x >> 5;
@@ -570,8 +594,10 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
     if (cnt_pos) {
       const uint32_t cs = chunk_start[tile / V3_TPC];
       const uint32_t smp = *(const uint32_t *)(samples + (size_t)tile * V3_SPT + 2u * lane);
-      sA = __ldg(F.applyF + (size_t)(smp & 0xFFFFu) * Q1 + cs);
-      if (cnt_pos > 16u) sB = __ldg(F.applyF + (size_t)(smp >> 16) * Q1 + cs);
+      const uint32_t bp = blockpre[(size_t)tile * (V3_TILE / V3_BLK) + (lane >> 2)];     // 4 lanes per 128-byte block
+      const uint32_t sblk = __ldg(F.applyF + (size_t)bp * Q1 + cs);
+      sA = __ldg(F.applyF + (size_t)(smp & 0xFFFFu) * Q1 + sblk);
+      if (cnt_pos > 16u) sB = __ldg(F.applyF + (size_t)(smp >> 16) * Q1 + sblk);
     }
     const uint32_t lam_tile = (REGS && active) ? lam_end[tile] : 0u;
 

@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/kexcuda.h"
@@ -655,7 +656,7 @@ struct Buf {
 // pipeline of kex_run_host can walk one sub-wave while the previous one emits.
 struct Ctx {
   Buf maps[8], starts[8], fates[8], lives[8];
-  Buf samples, pend, resolved, fail, outlen, outoff, bsum, res_dev;
+  Buf samples, blockpre, pend, resolved, fail, outlen, outoff, bsum, res_dev;
   Buf bmaps[8], lams[8], desc, ctl;
   FastCtl *ctl_host = nullptr;
   RunResult *res_host = nullptr;
@@ -715,8 +716,8 @@ static uint32_t rd32(const uint8_t *b, size_t off) {
 
 // Derived tables of the warp-autonomous kernels (kex_v3.cuh).  Programs whose
 // tables exceed the kernels' packed fields stay on the kex_fast.cuh kernels.
-static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const uint32_t *BE, const uint32_t *tplinfo,
-                   uint32_t NM) {
+static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const uint16_t *applyF, const uint32_t *BE,
+                   const uint32_t *tplinfo, uint32_t NM) {
   V3Dev &v = ph.v3;
   memset(&v, 0, sizeof(v));
   if (getenv("KEX_NO_V3")) return KEX_OK;
@@ -790,16 +791,38 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
   ph.smem_fwd3 = 512 + ((fwd.size() * 2 + 15) & ~(size_t)15);
   ph.smem_seams3 = 256 + 4ull * Q1 * C + (size_t)NB * F.NG + NB + 16;
   if (ph.smem_fwd3 > 200 * 1024 || ph.smem_seams3 > 200 * 1024) return KEX_OK;
-  const size_t o_be = 0, o_tp = o_be + 4ull * NE, o_fw = (o_tp + 4ull * NE + 15) & ~(size_t)15, tot = o_fw + fwd.size() * 2;
+  // element composition table: comp[a][b] = element of "a, then b" (the forward pass composes the
+  // elements of the 128-byte blocks of a chunk across a warp)
+  if (NM > 2048) return KEX_OK;
+  std::vector<uint16_t> comp((size_t)NM * NM);
+  {
+    std::unordered_map<std::string, uint16_t> index;
+    index.reserve(NM * 2);
+    for (uint32_t m = 0; m < NM; ++m)
+      index.emplace(std::string((const char *)(applyF + (size_t)m * Q1), Q1 * sizeof(uint16_t)), (uint16_t)m);
+    std::vector<uint16_t> t(Q1);
+    for (uint32_t a = 0; a < NM; ++a)
+      for (uint32_t b = 0; b < NM; ++b) {
+        for (uint32_t q = 0; q < Q1; ++q) t[q] = applyF[(size_t)b * Q1 + applyF[(size_t)a * Q1 + q]];
+        auto it = index.find(std::string((const char *)t.data(), Q1 * sizeof(uint16_t)));
+        if (it == index.end()) return KEX_ERR_BAD_BLOB;          // the element set is not closed
+        comp[(size_t)a * NM + b] = it->second;
+      }
+  }
+  v.NM = NM;
+  const size_t o_be = 0, o_tp = o_be + 4ull * NE, o_fw = (o_tp + 4ull * NE + 15) & ~(size_t)15,
+               o_cp = (o_fw + fwd.size() * 2 + 15) & ~(size_t)15, tot = o_cp + comp.size() * 2;
   std::vector<uint8_t> img(tot, 0);
   memcpy(img.data() + o_be, be3.data(), 4ull * NE);
   memcpy(img.data() + o_tp, tpl2.data(), 4ull * NE);
   memcpy(img.data() + o_fw, fwd.data(), fwd.size() * 2);
+  memcpy(img.data() + o_cp, comp.data(), comp.size() * 2);
   CK(cudaMalloc(&ph.d_v3, tot));
   CK(cudaMemcpy(ph.d_v3, img.data(), tot, cudaMemcpyHostToDevice));
   v.be3 = (const uint32_t *)((const uint8_t *)ph.d_v3 + o_be);
   v.tpl2 = (const uint32_t *)((const uint8_t *)ph.d_v3 + o_tp);
   v.fwdtab = (const uint16_t *)((const uint8_t *)ph.d_v3 + o_fw);
+  v.compF = (const uint16_t *)((const uint8_t *)ph.d_v3 + o_cp);
   v.ok = 1;
   return KEX_OK;
 }
@@ -870,7 +893,7 @@ static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph
   d.pool = db + off[10];
   ph.smem_ef_tables = tables;
   ph.fast = true;
-  return load_v3(p, ph, mulF, BE, tplinfo, NM);
+  return load_v3(p, ph, mulF, applyF, BE, tplinfo, NM);
 }
 
 static int load_phase(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
@@ -1014,7 +1037,7 @@ extern "C" void kex_free(kex_program *p) {
       cudaFree(c.maps[i].p); cudaFree(c.starts[i].p); cudaFree(c.fates[i].p); cudaFree(c.lives[i].p);
       cudaFree(c.bmaps[i].p); cudaFree(c.lams[i].p);
     }
-    Buf *bs[] = {&c.samples, &c.pend, &c.resolved, &c.fail, &c.outlen, &c.outoff, &c.bsum, &c.res_dev, &c.desc, &c.ctl};
+    Buf *bs[] = {&c.samples, &c.blockpre, &c.pend, &c.resolved, &c.fail, &c.outlen, &c.outoff, &c.bsum, &c.res_dev, &c.desc, &c.ctl};
     for (Buf *b : bs) cudaFree(b->p);
     if (c.ctl_host) cudaFreeHost(c.ctl_host);
     if (c.res_host) cudaFreeHost(c.res_host);
@@ -1292,20 +1315,21 @@ static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in
   if ((rc = ensure(p, p->c->samples, nchunks * (ph.v3.ok ? V3_SPC : KEX_NT) * sizeof(uint16_t)))) return rc;
   if (p->timing) CK(cudaEventRecord(p->ev[0], st));
   if (ph.v3.ok) {
-    // two chunks per thread, grid-stride over resident CTAs (the table is staged once per CTA)
+    // one warp per pair of chunks, grid-stride over resident CTAs (the table is staged once per CTA)
+    if ((rc = ensure(p, p->c->blockpre, nchunks * V3_BPC * sizeof(uint16_t)))) return rc;
     const size_t npairs = (nchunks + 1) / 2;
-    const unsigned ft = npairs >= 512u * (size_t)p->num_sms ? 512u : 128u;     // small inputs: spread over the SMs
-    size_t ctas = (npairs + ft - 1) / ft;
+    const unsigned ft = 512u;
+    size_t ctas = (npairs + ft / 32 - 1) / (ft / 32);
     size_t per_sm = (size_t)V3_SMEM_MAX / (ph.smem_fwd3 + 1024);
-    if (per_sm > 2048u / ft) per_sm = 2048u / ft;
+    if (per_sm > 2u) per_sm = 2u;                  // __launch_bounds__ of k3_fwd
     const size_t resident = (size_t)p->num_sms * (per_sm < 1 ? 1 : per_sm);
     if (ctas > resident) ctas = resident;
     if (ph.v3.pair)
       k3_fwd<true><<<(unsigned)ctas, ft, ph.smem_fwd3, st>>>(P, ph.fdev, ph.v3, d_in, n, nchunks, (uint16_t *)p->c->samples.p,
-                                                             (uint16_t *)p->c->maps[0].p);
+                                                            (uint16_t *)p->c->blockpre.p, (uint16_t *)p->c->maps[0].p);
     else
       k3_fwd<false><<<(unsigned)ctas, ft, ph.smem_fwd3, st>>>(P, ph.fdev, ph.v3, d_in, n, nchunks, (uint16_t *)p->c->samples.p,
-                                                              (uint16_t *)p->c->maps[0].p);
+                                                             (uint16_t *)p->c->blockpre.p, (uint16_t *)p->c->maps[0].p);
   } else {
     k_fwd_monoid<<<(unsigned)((nchunks + 127) / 128), 128, ph.smem_fm, st>>>(P, ph.fdev, d_in, n, nchunks,
                                                                             (uint16_t *)p->c->samples.p, (uint16_t *)p->c->maps[0].p);
@@ -1344,7 +1368,7 @@ static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st) {
     CK(cudaMemsetAsync(p->c->res_dev.p, 0xFF, sizeof(unsigned long long), st));     // fail_pos = none
     if (p->timing) CK(cudaEventRecord(p->ev[2], st));
     k3_seams<<<(unsigned)((ntiles + 255) / 256), 256, ph.smem_seams3, st>>>(
-        P, ph.fdev, p->c->sh_in, n, ntiles, (const uint16_t *)p->c->samples.p, (const uint16_t *)p->c->starts[0].p,
+        P, ph.fdev, p->c->sh_in, n, ntiles, (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p,
         (const uint16_t *)p->c->maps[0].p, (uint8_t *)p->c->bmaps[0].p, (RunResult *)p->c->res_dev.p);
     p->launches++;
     if (p->timing) CK(cudaEventRecord(p->ev[3], st));
@@ -1438,7 +1462,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
 #define V3_LAUNCH(LOGV, REGSV)                                                                                      \
     k3_emit<LOGV, REGSV><<<(unsigned)ctas, nwarp * 32u, smem3, st>>>(                                               \
         P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,                           \
-        (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p, (unsigned long long *)p->c->desc.p,           \
+        (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p, (unsigned long long *)p->c->desc.p,           \
         (FastCtl *)p->c->ctl.p, d_out, out_cap, (unsigned long long)p->emit_out_off, ph.v3_stage, warp_bytes)
     if (V.log == 7) { if (NL > 1) V3_LAUNCH(7, true); else V3_LAUNCH(7, false); }
     else { if (NL > 1) V3_LAUNCH(5, true); else V3_LAUNCH(5, false); }
