@@ -6,6 +6,13 @@
 // crt/crt.c) is evaluated here as a prefix computation over the SST's
 // transition monoid (src/KMC/SymbolicSST.hs:122-136):
 //
+// Three kernel families implement the same pipeline behind the C ABI; kex_load
+// picks the fastest one whose packed table fields fit the program:
+//   kex_v3.cuh    k3_fwd / k3_seams / k3_emit: monoid tables, warp-autonomous
+//                 emit (per-lane replicated tables, scan warp, swizzled staging)
+//   kex_fast.cuh  k_fwd_monoid / k_seams / k_emit_fast: monoid tables, CTA tiles
+//   this file     the generic kernels below (any copyless SST <= 32 registers):
+//
 //   k_chunk_maps   K1  per 4 KiB chunk: state map Q -> Q, speculating over all
 //                      start states with converging tracks   (readnext/consume
 //                      + the state chain of matchN, run for every start state)
