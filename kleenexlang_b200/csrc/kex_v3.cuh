@@ -691,6 +691,8 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       if (nt < ntiles) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(in + nt * V3_TILE + lane * 32u));
         if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(samples + nt * V3_SPT + lane * 16u));
+        if (lane == 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blockpre + nt * (V3_TILE / V3_BLK)));
+        if (REGS && lane == 5u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lam_end + nt));
       }
     }
     __threadfence_block();
