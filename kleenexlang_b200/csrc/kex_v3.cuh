@@ -228,22 +228,38 @@ k3_fwd(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n,
 }
 
 // ------------------------------------------------------------------ k3_seams
-// One thread per 1 KiB tile.  Shared memory: cls[256], trans2 u32 [(Q+1)*C],
-// mulB u8 [NB*NG], constB [NB].
+// One thread per 1 KiB tile.  Shared memory: cls4[256] (4 * class), transition
+// table u32 [(Q+1)*C] = byte offset of the next state's row | byte offset of the
+// generator inside a backward-element row << 16 | FAIL << 31, backward-element
+// table u16 [NB][NG] = byte offset of the product's row | constant-map << 15.
+// A step is LDS.U8 + LDS + LDS.U16 and a handful of integer instructions.
+#define S3_STEP(word, k)                                                                          \
+  {                                                                                               \
+    const uint32_t e = *(const uint32_t *)(tr + srow + cls4[byte_at(word, k)]);                   \
+    if ((int)e < 0) { fail_at = g + (uint32_t)(pos); goto seam_done; }                            \
+    srow = e & 0xFFFFu;                                                                           \
+    const uint32_t m = *(const uint16_t *)(mb2 + mrow + ((e >> 16) & 0x7FFFu));                   \
+    mrow = m & 0x7FFFu;                                                                           \
+    if ((m & 0x8000u) && !failing) goto seam_done;                                                \
+  }
 __global__ void __launch_bounds__(256)
 k3_seams(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n, size_t ntiles,
          const uint16_t *__restrict__ blockpre, const uint16_t *__restrict__ chunk_start,
          const uint16_t *__restrict__ maps, uint8_t *__restrict__ bmaps, RunResult *__restrict__ res) {
   extern __shared__ __align__(16) uint8_t smem_s3[];
   const uint32_t Q = P.Q, Q1 = Q + 1, C = P.C, NL = F.NL, NG = F.NG, NB = F.NB;
-  uint8_t *cls = smem_s3;
-  uint32_t *tr = (uint32_t *)(smem_s3 + 256);
-  uint8_t *mulB = smem_s3 + 256 + 4u * Q1 * C;
-  uint8_t *constB = mulB + NB * NG;
-  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cls[i] = P.cls[i];
-  for (uint32_t i = threadIdx.x; i < Q1 * C; i += blockDim.x) tr[i] = F.trans2[i];
-  for (uint32_t i = threadIdx.x; i < NB * NG; i += blockDim.x) mulB[i] = F.mulB[i];
-  for (uint32_t i = threadIdx.x; i < NB; i += blockDim.x) constB[i] = F.constB[i];
+  uint8_t *cls4 = smem_s3;
+  uint8_t *tr = smem_s3 + 256;
+  uint8_t *mb2 = tr + 4u * Q1 * C;
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cls4[i] = (uint8_t)(4u * P.cls[i]);
+  for (uint32_t i = threadIdx.x; i < Q1 * C; i += blockDim.x) {
+    const uint32_t e = F.trans2[i], nx = e & 0xFFFFu;
+    ((uint32_t *)tr)[i] = (nx * C * 4u) | ((e >> 24) * 2u) << 16 | (nx == Q ? 0x80000000u : 0u);
+  }
+  for (uint32_t i = threadIdx.x; i < NB * NG; i += blockDim.x) {
+    const uint32_t nx = F.mulB[i];
+    ((uint16_t *)mb2)[i] = (uint16_t)((nx * NG * 2u) | (F.constB[nx] ? 0x8000u : 0u));
+  }
   __syncthreads();
   const size_t tile = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= ntiles) return;
@@ -258,34 +274,77 @@ k3_seams(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n, size_t
   }
   if (tile == ntiles - 1) res->end_state = endst;
   const bool failing = (s != Q) && (endst == Q);
-  uint32_t mb = 0;
+  uint32_t mrow = 0, fail_at = KEX_NONE32;
+  const size_t base = tile * V3_TILE;
   if (s != Q && (failing || NL > 1)) {
-    const size_t base = tile * V3_TILE;
     const uint32_t len = (uint32_t)((n - base < V3_TILE) ? (n - base) : V3_TILE);
     const uint8_t *p = in + base;
-    bool done = false;
-    for (uint32_t g = 0; g < len && !done; g += 16) {
+    uint32_t srow = s * C * 4u;
+    uint32_t g = 0;
+    for (; g + 16u <= len; g += 16u) {
       const uint4 v = *(const uint4 *)(p + g);
-      const uint32_t lim = (len - g < 16u) ? (len - g) : 16u;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        if (!done && (uint32_t)k < lim) {
-          const uint32_t e = tr[s * C + cls[byte_at(word_of(v, k >> 2), k & 3)]];
-          const uint32_t ns = e & 0xFFFFu;
-          if (ns == Q) {
-            atomicMin(&res->fail_pos, (unsigned long long)(base + g + k));
-            done = true;
-          } else {
-            s = ns;
-            mb = mulB[mb * NG + (e >> 24)];
-            if (!failing && constB[mb]) done = true;
-          }
-        }
-      }
+#define pos 0
+      S3_STEP(v.x, 0)
+#undef pos
+#define pos 1
+      S3_STEP(v.x, 1)
+#undef pos
+#define pos 2
+      S3_STEP(v.x, 2)
+#undef pos
+#define pos 3
+      S3_STEP(v.x, 3)
+#undef pos
+#define pos 4
+      S3_STEP(v.y, 0)
+#undef pos
+#define pos 5
+      S3_STEP(v.y, 1)
+#undef pos
+#define pos 6
+      S3_STEP(v.y, 2)
+#undef pos
+#define pos 7
+      S3_STEP(v.y, 3)
+#undef pos
+#define pos 8
+      S3_STEP(v.z, 0)
+#undef pos
+#define pos 9
+      S3_STEP(v.z, 1)
+#undef pos
+#define pos 10
+      S3_STEP(v.z, 2)
+#undef pos
+#define pos 11
+      S3_STEP(v.z, 3)
+#undef pos
+#define pos 12
+      S3_STEP(v.w, 0)
+#undef pos
+#define pos 13
+      S3_STEP(v.w, 1)
+#undef pos
+#define pos 14
+      S3_STEP(v.w, 2)
+#undef pos
+#define pos 15
+      S3_STEP(v.w, 3)
+#undef pos
     }
+    for (; g < len; ++g) {
+      const uint32_t w1 = p[g];
+#define pos 0
+      S3_STEP(w1, 0)
+#undef pos
+    }
+  seam_done:;
   }
-  if (NL > 1)
+  if (fail_at != KEX_NONE32) atomicMin(&res->fail_pos, (unsigned long long)(base + fail_at));
+  if (NL > 1) {
+    const uint32_t mb = mrow / (NG * 2u);
     for (uint32_t l = 0; l < NL; ++l) bmaps[tile * NL + l] = __ldg(F.applyB + mb * NL + l);
+  }
 }
 
 // ------------------------------------------------------------------ k3_emit

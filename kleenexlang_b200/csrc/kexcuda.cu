@@ -796,7 +796,7 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
     }
   v.fwd_entries = (uint32_t)fwd.size();
   ph.smem_fwd3 = 512 + ((fwd.size() * 2 + 15) & ~(size_t)15);
-  ph.smem_seams3 = 256 + 4ull * Q1 * C + (size_t)NB * F.NG + NB + 16;
+  ph.smem_seams3 = 256 + 4ull * Q1 * C + 2ull * NB * F.NG + 16;
   if (ph.smem_fwd3 > 200 * 1024 || ph.smem_seams3 > 200 * 1024) return KEX_OK;
   // element composition table: comp[a][b] = element of "a, then b" (the forward pass composes the
   // elements of the 128-byte blocks of a chunk across a warp)
