@@ -113,6 +113,11 @@ int kex_shard_emit(kex_program *p, uint32_t seam_code, size_t n_eff,
 int kex_final_action(const kex_program *p, uint32_t state, int *accepting,
                      uint32_t *seam_code, const uint8_t **tail, size_t *tail_len);
 
+/* Replaces `-p N` / `--phase N` of the compiled binary (crt/crt.c:380-399,
+ * 356-364): the following kex_run_* calls evaluate only phase `phase`
+ * (1-based, as the reference numbers them); 0 = the whole pipeline (default). */
+int kex_select_phase(kex_program *p, uint32_t phase);
+
 /* Upper bound on the output size for n input bytes (all phases). */
 size_t kex_out_bound(const kex_program *p, size_t n);
 

@@ -692,6 +692,7 @@ struct kex_program {
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> pipe_ev;
   size_t emit_out_off = 0;            // v3 emit: offset of this shard's output inside d_out
+  uint32_t only_phase = 0;            // 1-based phase selected by kex_select_phase, 0 = all
 };
 
 #define CK(call)                                                              \
@@ -1106,6 +1107,11 @@ extern "C" size_t kex_out_bound(const kex_program *p, size_t n) {
   return cur;
 }
 
+extern "C" int kex_select_phase(kex_program *p, uint32_t phase) {
+  if (!p || phase > p->phases.size()) return KEX_ERR_ARG;
+  p->only_phase = phase;
+  return KEX_OK;
+}
 extern "C" uint32_t kex_last_launch_count(const kex_program *p) { return p ? p->launches : 0; }
 extern "C" int kex_set_timing(kex_program *p, int enabled) { if (!p) return KEX_ERR_ARG; p->timing = enabled != 0; return KEX_OK; }
 extern "C" float kex_last_kernel_ms(const kex_program *p, uint32_t which) { return (p && which < 4) ? p->ms[which] : 0.f; }
@@ -1693,8 +1699,9 @@ extern "C" int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n, uin
   if (p->timing) CK(cudaEventRecord(p->ev[6], st));
   const uint8_t *cur = d_in;
   size_t cur_n = n;
-  const size_t nph = p->phases.size();
-  for (size_t i = 0; i < nph; ++i) {
+  const size_t first = p->only_phase ? p->only_phase - 1 : 0;
+  const size_t nph = p->only_phase ? p->only_phase : p->phases.size();
+  for (size_t i = first; i < nph; ++i) {
     uint8_t *dst = d_out;
     size_t cap = out_cap;
     if (i + 1 < nph) {
@@ -1881,7 +1888,7 @@ extern "C" int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n, uint8
   if ((rc = ensure(p, p->hostio_out, out_cap + 16))) return rc;
   size_t wave = 128u << 20;
   if (const char *e = getenv("KEX_HOST_WAVE_MIB")) { const long x = atol(e); if (x > 0) wave = (size_t)x << 20; }
-  if (p->phases.size() == 1 && p->phases[0].v3.ok && n >= 2 * wave && !getenv("KEX_NO_HOST_PIPELINE")) {
+  if (p->phases.size() == 1 && p->phases[0].v3.ok && n >= 2 * wave && !getenv("KEX_NO_HOST_PIPELINE")) {   // (a selected phase of a 1-phase program is that phase)
     rc = run_host_pipelined(p, h_in, n, h_out, out_cap, out_len, status, fail_count, wave);
     if (rc <= 0 && rc != KEX_ERR_OUT_CAP) return rc;
     // the pipeline gave up (or the output did not fit): evaluate the resident input at once

@@ -30,7 +30,8 @@ class KexInfo(ctypes.Structure):
 
 
 EXPORTS = ["kex_load", "kex_free", "kex_info", "kex_run_device", "kex_run_host", "kex_shard_summarize",
-           "kex_seam_bytes", "kex_shard_walk", "kex_stitch_live", "kex_shard_emit", "kex_final_action", "kex_out_bound", "kex_last_launch_count",
+           "kex_seam_bytes", "kex_shard_walk", "kex_stitch_live", "kex_shard_emit", "kex_final_action", "kex_out_bound",
+           "kex_select_phase", "kex_last_launch_count",
            "kex_set_timing", "kex_last_kernel_ms", "kex_strerror", "kex_last_cuda_error"]
 
 
@@ -62,6 +63,7 @@ def lib():
     L.kex_stitch_live.argtypes = [vp, ctypes.c_char_p, sz, u32, ctypes.POINTER(u32)]
     L.kex_final_action.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(u32),
                                    ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz)]
+    L.kex_select_phase.argtypes = [vp, u32]
     L.kex_out_bound.argtypes = [vp, sz]
     L.kex_out_bound.restype = sz
     L.kex_last_launch_count.argtypes = [vp]
@@ -125,6 +127,11 @@ class CompiledProgram:
 
     def out_bound(self, n):
         return self._L.kex_out_bound(self._h, n)
+
+    def select_phase(self, phase=0):
+        """`--phase N` of the compiled binary: later runs evaluate only phase N
+        (1-based); 0 = the whole pipeline."""
+        self._check(self._L.kex_select_phase(self._h, phase))
 
     def set_timing(self, on=True):
         self._L.kex_set_timing(self._h, 1 if on else 0)

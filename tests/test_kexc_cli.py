@@ -1,0 +1,95 @@
+"""`kexc` command-line surface (src/kexc.hs:13-27, Options.hs:146-201) and the
+process contract of the produced binary (crt/crt.c:372-467).  The CPU part
+needs no GPU: flag spellings, artefacts, `-h`/`-i` exit codes, `simulate`.
+The GPU part pipes inputs through the launcher as
+test/test_compiled/runtest.sh:21-26 does."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT, PROGRAMS, load_vectors, vec_matches
+
+KEXC = [sys.executable, "-m", "kleenexlang_b200.kexc"]
+ENV = dict(os.environ, PYTHONPATH=ROOT)
+
+
+def _compile(tmp_path, name, *flags):
+    out = str(tmp_path / name)
+    r = subprocess.run(KEXC + ["compile", os.path.join(PROGRAMS, name + ".kex"), "--out", out, *flags],
+                       capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+def test_compile_writes_blob_and_launcher(tmp_path):
+    out = _compile(tmp_path, "add-commas", "--opt", "0", "--la=false", "--act=false", "--quiet",
+                   "--srcout", str(tmp_path / "src.txt"))
+    assert os.path.exists(out + ".kexprog") and os.access(out, os.X_OK)
+    assert "SST states" in open(tmp_path / "src.txt").read()
+    h = subprocess.run([out, "-h"], capture_output=True)
+    assert h.returncode == 1 and b"-t" in h.stdout            # RETC_PRINT_USAGE, crt/crt.c:14
+    i = subprocess.run([out, "-i"], capture_output=True)
+    assert i.returncode == 2 and b"--opt 0" in i.stdout       # RETC_PRINT_INFO, crt/crt.c:15
+    assert subprocess.run([out, "--bogus"], capture_output=True).returncode == 1
+
+
+def test_reference_default_flags_are_accepted(tmp_path):
+    # `kexc compile prog.kex --out bin` with the reference's defaults (--la=true --act=true)
+    out = str(tmp_path / "t")
+    r = subprocess.run(KEXC + ["compile", os.path.join(PROGRAMS, "thousand_sep.kex"), "--out", out],
+                       capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 0 and b"--la=false" in r.stderr
+
+
+def test_usage_without_subcommand():
+    r = subprocess.run(KEXC, capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 1 and b"compile" in r.stdout
+
+
+@pytest.mark.parametrize("sim", ["lockstep", "sst"])
+def test_simulate_readme_example(sim):
+    # README.md:36-42
+    r = subprocess.run(KEXC + ["simulate", "--quiet", "--sim=" + sim, os.path.join(PROGRAMS, "add-commas.kex")],
+                       input=b"2016\n", capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 0 and r.stdout == b"2,016\n"
+
+
+def test_simulate_apache_log_config():
+    # BASELINE config 1: apache_log.kex via `kexc simulate` on the bundled log sample (CPU)
+    from conftest import sample
+    from kleenexlang_b200.frontend.driver import build_ssts
+    from oracle.sstbin import oracle_run
+    d = sample("apache_sample.log")
+    r = subprocess.run(KEXC + ["simulate", "--quiet", os.path.join(PROGRAMS, "apache_log.kex")],
+                       input=d, capture_output=True, cwd=ROOT, env=ENV)
+    src = open(os.path.join(PROGRAMS, "apache_log.kex"), encoding="utf-8").read()
+    est, eout, _ = oracle_run(build_ssts(src), d)
+    assert r.returncode == est == 0 and r.stdout == eout
+
+
+@pytest.mark.gpu
+def test_compiled_binary_contract(tmp_path):
+    vecs = [v for v in load_vectors() if not v["uses_registers"]][:12]
+    for k, v in enumerate(vecs):
+        src = tmp_path / ("p%d.kex" % k)
+        src.write_text(v["program"], encoding="utf-8")
+        out = str(tmp_path / ("p%d" % k))
+        c = subprocess.run(KEXC + ["compile", str(src), "--out", out, "--opt", "0", "--la=false", "--quiet"],
+                           capture_output=True, cwd=ROOT, env=ENV)
+        if c.returncode == 1 and b"exceeds a limit" in c.stderr:
+            continue                                          # > 32 simultaneously live registers
+        assert c.returncode == 0, c.stderr
+        r = subprocess.run([out], input=v["input"], capture_output=True)
+        assert r.returncode == 0 and vec_matches(v, r.stdout), v["name"]
+    out = _compile(tmp_path, "csv2json", "--quiet")
+    from conftest import sample
+    d = sample("csv_sample.csv")
+    ok = subprocess.run([out, "-t"], input=d, capture_output=True)
+    assert ok.returncode == 0 and ok.stderr.startswith(b"time (ms): ")
+    ph = subprocess.run([out, "-p", "1"], input=d, capture_output=True)
+    assert ph.returncode == 0 and ph.stdout == ok.stdout
+    cut = d.index(b"\n", 100) + 2                            # inside the numeric id of a later row
+    bad = subprocess.run([out], input=d[:cut] + b"x" + d[cut + 1:], capture_output=True)
+    assert bad.returncode == 1 and bad.stderr == b"Match error at input symbol %d!\n" % cut
