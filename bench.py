@@ -84,34 +84,41 @@ def ref_binary():
     return p if os.path.exists(p) else None
 
 
-def time_reference(sample_bytes, instances):
-    """Times `instances` copies of the reference's compiled C binary
-    (oracle/_ref, emitted C + verbatim crt.c, `cc -O3 -D FLAG_WORDALIGNED`),
-    each on its own record-aligned file in /dev/shm, stdout to /dev/null as
-    bench/runningtime.sh:101 does.  Returns (seconds, total input bytes)."""
+def make_reference_inputs(sample_bytes, instances):
+    """One record-aligned CSV file per instance in /dev/shm (written once, reused by every step)."""
     from kleenexlang_b200 import workloads
-    binp = ref_binary()
-    files = []
-    total = 0
     block = workloads.gen_csv(min(sample_bytes, 64 << 20), seed=1234)
     reps = max(1, sample_bytes // len(block))
+    files = []
     for i in range(instances):
         f = "/dev/shm/kexbench_%d_%d.csv" % (os.getpid(), i)
         with open(f, "wb") as fh:
             for _ in range(reps):
                 fh.write(block.tobytes())
         files.append(f)
-        total += reps * len(block)
+    return files, reps * len(block) * instances
+
+
+def run_reference_once(files):
+    """Times one concurrent pass of the reference's compiled C binary
+    (oracle/_ref, emitted C + verbatim crt.c, `cc -O3 -D FLAG_WORDALIGNED`) over
+    the files, stdout to /dev/null as bench/runningtime.sh:101 does."""
+    binp = ref_binary()
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([binp], stdin=open(f, "rb"), stdout=subprocess.DEVNULL) for f in files]
+    rcs = [p.wait() for p in procs]
+    dt = time.perf_counter() - t0
+    assert all(rc == 0 for rc in rcs), "reference binary rejected the synthetic CSV"
+    return dt
+
+
+def time_reference(sample_bytes, instances):
+    files, total = make_reference_inputs(sample_bytes, instances)
     try:
-        t0 = time.perf_counter()
-        procs = [subprocess.Popen([binp], stdin=open(f, "rb"), stdout=subprocess.DEVNULL) for f in files]
-        rcs = [p.wait() for p in procs]
-        dt = time.perf_counter() - t0
-        assert all(rc == 0 for rc in rcs), "reference binary rejected the synthetic CSV"
+        return run_reference_once(files), total
     finally:
         for f in files:
             os.unlink(f)
-    return dt, total
 
 
 def time_oracle_port(sample_bytes):
@@ -145,16 +152,22 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per = 256 << 20
-    vals = []
     kind = "reference" if ref_binary() else "port"
-    for i in range(args.warmup + args.steps):
-        if kind == "reference":
-            dt, nb = time_reference(per, cores)
-        else:
-            dt, nb = time_oracle_port(32 << 20)
-        if i >= args.warmup:
-            vals.append((dt, nb))
+    # bounded sample: at most ~8 GiB of /dev/shm over all processes, 64-256 MiB each
+    per = max(64 << 20, min(256 << 20, (8 << 30) // cores))
+    vals = []
+    files, total = make_reference_inputs(per, cores) if kind == "reference" else ([], 0)
+    try:
+        for i in range(args.warmup + args.steps):
+            if kind == "reference":
+                dt, nb = run_reference_once(files), total
+            else:
+                dt, nb = time_oracle_port(32 << 20)
+            if i >= args.warmup:
+                vals.append((dt, nb))
+    finally:
+        for f in files:
+            os.unlink(f)
     tot_t = sum(v[0] for v in vals)
     tot_b = sum(v[1] for v in vals)
     value = tot_b / GIB / tot_t
