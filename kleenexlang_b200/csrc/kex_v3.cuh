@@ -83,6 +83,23 @@ __device__ __forceinline__ uint32_t lds_u8_v(uint32_t a) {
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
+// The live-set guess table of k3_emit is read and written without
+// synchronisation on purpose (any value is only a guess that the count pass
+// verifies); built with -DKEX_SANITIZE the helpers are not inlined, which keeps
+// these accesses apart in compute-sanitizer reports (profiles/r01_sanitizer.txt).
+#ifdef KEX_SANITIZE
+#define KEX_GUESS_FN __noinline__
+#else
+#define KEX_GUESS_FN __forceinline__
+#endif
+__device__ KEX_GUESS_FN uint32_t guess_ld(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ KEX_GUESS_FN void guess_st(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 // acc - (byte 0 of e): unsigned bytes of e times signed bytes (-1, 0, 0, 0)
 __device__ __forceinline__ uint32_t sub_byte0(uint32_t e, uint32_t acc) {
   int r;
@@ -678,8 +695,8 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       gix = sB | (__shfl_down_sync(0xFFFFFFFFu, sA, 1) << 16);
       spec = full && (int)spec_ctr >= 0;
       if (spec) {
-        const uint32_t gH = lds_u8_v(guess_abs + (gix & 0xFFFFu));
-        const uint32_t gT = (lane == 31u) ? lam_tile : lds_u8_v(guess_abs + (gix >> 16));
+        const uint32_t gH = guess_ld(guess_abs + (gix & 0xFFFFu));
+        const uint32_t gT = (lane == 31u) ? lam_tile : guess_ld(guess_abs + (gix >> 16));
         spec = __all_sync(0xFFFFFFFFu, gH != 0xFFu && gT != 0xFFu);
         ELA = (gH * A) << 24;
         ELB = (gT * A) << 24;
@@ -716,8 +733,8 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
         lamH = applyB[mbB * NL + lamT];
         if (full) {
           // learn from an exactly evaluated tile
-          sts_u8(guess_abs + (gix & 0xFFFFu), lamH);
-          if (lane != 31u) sts_u8(guess_abs + (gix >> 16), lamT);
+          guess_st(guess_abs + (gix & 0xFFFFu), lamH);
+          if (lane != 31u) guess_st(guess_abs + (gix >> 16), lamT);
         }
       }
       ELA = (lamH * A) << 24;
