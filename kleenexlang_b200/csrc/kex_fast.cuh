@@ -39,7 +39,7 @@ struct FastCtl {                 // device control block of one emit launch
   unsigned int ticket;
   unsigned int error;            // look-back gave up (should never happen)
   unsigned int overflow;         // output would exceed out_cap
-  unsigned int pad;
+  unsigned int pad;              // v3: most template records any tile had
   unsigned long long total_out;
 };
 

@@ -31,7 +31,7 @@
 #define V3_SPC (KEX_CHUNK / V3_SUB)     // samples per 4 KiB chunk (256)
 #define V3_SPT (V3_TILE / V3_SUB)       // samples per tile (64)
 #define V3_TPC (KEX_CHUNK / V3_TILE)    // tiles per chunk (4)
-#define V3_RECCAP 192u                  // template records per tile kept in shared memory
+#define V3_RECCAP 192u                  // template records per tile kept in shared memory (first run; then adaptive)
 #define V3_SMEM_MAX (227 * 1024)        // dynamic shared memory per CTA on sm_100
 
 struct V3Dev {
@@ -515,7 +515,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
         const uint16_t *__restrict__ chunk_start, const uint8_t *__restrict__ lam_end,
         unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl, uint8_t *__restrict__ out, size_t out_cap,
         unsigned long long out_off, uint32_t stage_bytes,
-        uint32_t warp_bytes) {
+        uint32_t warp_bytes, uint32_t reccap) {
   constexpr uint32_t STRIDE = 1u << LOG, REP = STRIDE / 4u;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const uint32_t Q = P.Q, Q1 = Q + 1, C = P.C, A = P.A, NL = F.NL, NB = F.NB, NG = F.NG;
@@ -646,6 +646,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
 
   // ================================================================= workers
   uint32_t prev_total = 0xFFFFFFFFu;                  // tile whose staging window has not left yet
+  uint32_t max_recs = 0;                              // most template records a tile of this warp had
   for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x, par ^= 1u) {
     const uint32_t tile = grp * nwork + warp;
     const bool active = tile < ntiles;
@@ -788,7 +789,8 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
     }
     const uint32_t o_end = xs & 0xFFFFFu;                        // bytes up to and including this thread
     const uint32_t rec_excl = (xs >> 20) - (nrA + nrB);
-    if (total + 16u <= stage_bytes && total_recs <= V3_RECCAP) {
+    max_recs = total_recs > max_recs ? total_recs : max_recs;
+    if (total + 16u <= stage_bytes && total_recs <= reccap) {
       // ---- write pass: input bytes into the staging window (tile-relative, so it
       // does not need the global offset), one record per template
       const uint32_t oB = stage_abs + o_end, oA = oB - cntB;
@@ -834,6 +836,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       __syncwarp();
     }
   }
+  if (lane == 0 && max_recs) atomicMax(&ctl->pad, max_recs);
   if (prev_total != 0xFFFFFFFFu) {
     // the last tile of this warp (par has advanced past its round)
     asm volatile("bar.sync %0, %1;" ::"r"(3u + (par ^ 1u)), "r"(bar_n) : "memory");

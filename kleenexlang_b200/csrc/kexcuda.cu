@@ -650,6 +650,7 @@ struct PhaseHost {
   void *d_v3 = nullptr;               // be3, tpl2, fwdtab
   size_t smem_fwd3 = 0, smem_seams3 = 0;
   uint32_t v3_stage = 3072;           // per-warp staging window; follows the observed out/in ratio
+  uint32_t v3_reccap = V3_RECCAP;     // template records per tile kept in shared memory; follows the observed maximum
   size_t tile() const { return v3.ok ? (size_t)V3_TILE : (size_t)KEX_CHUNK; }
 };
 
@@ -1452,7 +1453,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     // staging windows leave room for); every CTA must be resident because groups
     // are assigned statically and chained in order
     const V3Dev &V = ph.v3;
-    const uint32_t warp_bytes = (ph.v3_stage + 128u + V3_RECCAP * 8u + 127u) & ~127u;
+    const uint32_t warp_bytes = (ph.v3_stage + 128u + ph.v3_reccap * 8u + 127u) & ~127u;
     uint32_t nwork = (uint32_t)(((size_t)V3_SMEM_MAX - V.o_warp) / warp_bytes);
     if (nwork > 31u) nwork = 31u;
     if (const char *e = getenv("KEX_V3_WORKERS")) { const uint32_t x = (uint32_t)atoi(e); if (x >= 1 && x < nwork) nwork = x; }
@@ -1476,7 +1477,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     k3_emit<LOGV, REGSV><<<(unsigned)ctas, nwarp * 32u, smem3, st>>>(                                               \
         P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,                           \
         (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p, (unsigned long long *)p->c->desc.p,           \
-        (FastCtl *)p->c->ctl.p, d_out, out_cap, (unsigned long long)p->emit_out_off, ph.v3_stage, warp_bytes)
+        (FastCtl *)p->c->ctl.p, d_out, out_cap, (unsigned long long)p->emit_out_off, ph.v3_stage, warp_bytes, ph.v3_reccap)
     if (V.log == 7) { if (NL > 1) V3_LAUNCH(7, true); else V3_LAUNCH(7, false); }
     else { if (NL > 1) V3_LAUNCH(5, true); else V3_LAUNCH(5, false); }
 #undef V3_LAUNCH
@@ -1494,7 +1495,12 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     uint32_t want = (uint32_t)(per_tile * 1.25) + 256;
     want = (want + 255u) & ~255u;
     if (want < 2048u) want = 2048u;
-    const uint32_t stage_max = (uint32_t)(((V3_SMEM_MAX - V.o_warp) / 8u - 128u - V3_RECCAP * 8u) & ~255u);   // keep >= 8 warps
+    // ... and the record slots from the most records a tile had
+    uint32_t wrec = (p->c->ctl_host->pad + p->c->ctl_host->pad / 4u + 32u + 63u) & ~63u;
+    if (wrec < V3_RECCAP) wrec = V3_RECCAP;
+    if (wrec > 1024u) wrec = 1024u;
+    if (wrec > ph.v3_reccap || wrec + 128u < ph.v3_reccap) ph.v3_reccap = wrec;
+    const uint32_t stage_max = (uint32_t)(((V3_SMEM_MAX - V.o_warp) / 8u - 128u - ph.v3_reccap * 8u) & ~255u);   // keep >= 8 warps
     if (want > stage_max) want = stage_max;
     if (want > ph.v3_stage || want + 1024u < ph.v3_stage) ph.v3_stage = want;
     return KEX_OK;
