@@ -186,6 +186,31 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index):
+    """Best effort: run this rank (and allocate its pinned host buffers) on the
+    NUMA node its GPU hangs off, so the end-to-end leg does not cross sockets."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(index), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -214,6 +239,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -365,7 +391,8 @@ def main():
                            "l2": "inputs (%.1f GiB) far exceed the 126 MB L2; no explicit flush" % (n / GIB),
                            "verified": "output == %d x the 64 MiB block's output, compared on the device after the timed "
                                        "region" % reps if verified else None,
-                           "parallelism": "1 shard per GPU, 2 all-gathers of seam summaries" if world > 1 else "1 GPU"},
+                           "parallelism": ("1 shard per GPU, 2 all-gathers of seam summaries; rank 0 bound to NUMA node %s"
+                                           % numa) if world > 1 else "1 GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
         if world == 1:
             emit_ms = kms[2] / args.steps
