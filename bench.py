@@ -226,6 +226,11 @@ def main():
         run_reference_arm(args)
         return
 
+    # libraries (NCCL's version banner) may write to stdout: keep fd 1 for the ONE JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -407,7 +412,8 @@ def main():
                                 "pipeline_frac": (n + expect_out) / (ms_per_step / 1000.0) / 1e9 / peak}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
