@@ -515,7 +515,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
         const uint16_t *__restrict__ chunk_start, const uint8_t *__restrict__ lam_end,
         unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl, uint8_t *__restrict__ out, size_t out_cap,
         unsigned long long out_off, uint32_t stage_bytes,
-        uint32_t warp_bytes, uint32_t reccap) {
+        uint32_t warp_bytes, uint32_t reccap, uint32_t nospec) {
   constexpr uint32_t STRIDE = 1u << LOG, REP = STRIDE / 4u;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const uint32_t Q = P.Q, Q1 = Q + 1, C = P.C, A = P.A, NL = F.NL, NB = F.NB, NG = F.NG;
@@ -581,7 +581,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
   const uint32_t bar_n = blockDim.x;
   uint32_t par = 0;
   const uint32_t guess_abs = base + V.o_guess;        // [Q+1] live set usually seen when a half ends in this state
-  uint32_t spec_ctr = 0;
+  uint32_t spec_ctr = nospec ? 0x80000000u : 0u;     // sign bit: evaluate every tile exactly
 
   if (warp == nwork) {
     // =============================================================== scan warp

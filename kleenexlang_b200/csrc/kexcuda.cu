@@ -1453,6 +1453,10 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     // staging windows leave room for); every CTA must be resident because groups
     // are assigned statically and chained in order
     const V3Dev &V = ph.v3;
+    // test knobs: force the slow paths (tiny staging window / record slots) or exact live sets
+    if (const char *e = getenv("KEX_V3_STAGE")) { const long x = atol(e); if (x >= 2048) ph.v3_stage = (uint32_t)x & ~255u; }
+    if (const char *e = getenv("KEX_V3_RECCAP")) { const long x = atol(e); if (x >= 8) ph.v3_reccap = (uint32_t)x; }
+    const uint32_t nospec = getenv("KEX_V3_NOSPEC") ? 1u : 0u;
     const uint32_t warp_bytes = (ph.v3_stage + 128u + ph.v3_reccap * 8u + 127u) & ~127u;
     uint32_t nwork = (uint32_t)(((size_t)V3_SMEM_MAX - V.o_warp) / warp_bytes);
     if (nwork > 31u) nwork = 31u;
@@ -1477,7 +1481,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     k3_emit<LOGV, REGSV><<<(unsigned)ctas, nwarp * 32u, smem3, st>>>(                                               \
         P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,                           \
         (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p, (unsigned long long *)p->c->desc.p,           \
-        (FastCtl *)p->c->ctl.p, d_out, out_cap, (unsigned long long)p->emit_out_off, ph.v3_stage, warp_bytes, ph.v3_reccap)
+        (FastCtl *)p->c->ctl.p, d_out, out_cap, (unsigned long long)p->emit_out_off, ph.v3_stage, warp_bytes, ph.v3_reccap, nospec)
     if (V.log == 7) { if (NL > 1) V3_LAUNCH(7, true); else V3_LAUNCH(7, false); }
     else { if (NL > 1) V3_LAUNCH(5, true); else V3_LAUNCH(5, false); }
 #undef V3_LAUNCH
@@ -1490,6 +1494,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     const size_t total = (size_t)p->c->ctl_host->total_out;
     *out_len = total;
     if (p->c->ctl_host->overflow || total + p->emit_out_off > out_cap) return KEX_ERR_OUT_CAP;
+    if (getenv("KEX_V3_STAGE") || getenv("KEX_V3_RECCAP")) return KEX_OK;
     // size the staging windows for the next run from the observed out/in ratio
     const double per_tile = (double)total / (double)ntiles;
     uint32_t want = (uint32_t)(per_tile * 1.25) + 256;

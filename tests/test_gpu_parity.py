@@ -239,3 +239,23 @@ def test_large_properties_tiled(name, block_mib, reps):
     # the same bytes through kex_run_host (sub-wave pipeline over three streams)
     st2, hout, _ = prog.run(bytes(big[: 8 * len(block)].cpu().numpy()))
     assert st2 == 0 and hout == eout * 8
+
+
+@pytest.mark.parametrize("name", PROGS)
+@pytest.mark.parametrize("knob", [{"KEX_V3_NOSPEC": "1"}, {"KEX_V3_STAGE": "2048", "KEX_V3_RECCAP": "8"},
+                                  {"KEX_NO_V3": "1"}])
+def test_v3_paths_forced(name, knob, monkeypatch):
+    """The rarely taken paths of the v3 kernels, forced: exact live sets for
+    every tile (no guessing), tiles that do not fit the staging window / record
+    slots (byte stores to global), and the CTA-tile monoid kernels that take
+    over when a program exceeds the v3 table limits."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    for k, v in knob.items():
+        monkeypatch.setenv(k, v)
+    prog = CompiledProgram(compile_kex(program_source(name)))          # KEX_NO_V3 is read at load time
+    ssts = build_ssts(program_source(name))
+    assert prog.info()["chunk_bytes"] == (4096 if "KEX_NO_V3" in knob else 1024)
+    d = workloads.GENERATORS[name](2 << 20, seed=61).tobytes()
+    _check(prog, ssts, d)
+    _check(prog, ssts, d[:700001])
+    _check(prog, ssts, d[:1000000] + b"\x01" + d[1000001:])
