@@ -380,7 +380,7 @@ def main():
     e2e = {"value": world * waves * wave_n * e2e_steps / GIB / dt, "unit": "GiB/s",
            "h2d_bytes_per_step": waves * wave_n, "d2h_bytes_per_step": waves * wave_out,
            "note": "kex_run_host over pinned host buffers, %d calls of %.2f GiB per step, %d steps; inside a call "
-                   "128 MiB sub-waves are copied in, evaluated and copied out on three streams" % (
+                   "64 MiB sub-waves are copied in, evaluated and copied out on three streams" % (
                waves, wave_n / GIB, e2e_steps)}
 
     if rank == 0:

@@ -621,6 +621,14 @@ __global__ void k_copy_tail(const uint8_t *__restrict__ src, uint32_t len, uint8
   for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
 }
 
+// small results (run summary, scan control block, state map, seam summary) go to
+// the host through mapped pinned memory instead of a device->host copy: a copy
+// would queue behind the output copies of kex_run_host's pipeline on the copy engine
+__global__ void k_publish(const uint8_t *__restrict__ src, volatile uint8_t *dst, uint32_t n) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
 #include "kex_fast.cuh"
 #include "kex_v3.cuh"
 
@@ -668,6 +676,7 @@ struct Ctx {
   Buf bmaps[8], lams[8], desc, ctl;
   FastCtl *ctl_host = nullptr;
   RunResult *res_host = nullptr;
+  uint8_t *hpub = nullptr, *dpub = nullptr;   // 4 KiB of mapped pinned memory (k_publish)
   // shard state between the three shard calls
   const uint8_t *sh_in = nullptr;
   size_t sh_n = 0, sh_nchunks = 0;
@@ -713,6 +722,20 @@ static int ensure(kex_program *p, Buf &b, size_t bytes) {
   size_t want = bytes + bytes / 8 + 256;
   CK(cudaMalloc(&b.p, want));
   b.cap = want;
+  return KEX_OK;
+}
+
+// device -> host of a few bytes, synchronising the stream
+static int fetch_sync(kex_program *p, void *h_dst, const void *d_src, size_t n, cudaStream_t st) {
+  if (p->c->hpub && n <= 4096) {
+    k_publish<<<1, 128, 0, st>>>((const uint8_t *)d_src, p->c->dpub, (uint32_t)n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    memcpy(h_dst, p->c->hpub, n);
+    return KEX_OK;
+  }
+  CK(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return KEX_OK;
 }
 
@@ -1030,6 +1053,12 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
   for (Ctx &c : p->cx) {
     if (cudaMallocHost((void **)&c.ctl_host, sizeof(FastCtl)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
     if (cudaMallocHost((void **)&c.res_host, sizeof(RunResult)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
+    if (cudaHostAlloc((void **)&c.hpub, 4096, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&c.dpub, c.hpub, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (c.hpub) cudaFreeHost(c.hpub);
+      c.hpub = c.dpub = nullptr;                       // fall back to copies
+    }
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&p->ev[i]);
   p->ev_ok = true;
@@ -1050,6 +1079,7 @@ extern "C" void kex_free(kex_program *p) {
     for (Buf *b : bs) cudaFree(b->p);
     if (c.ctl_host) cudaFreeHost(c.ctl_host);
     if (c.res_host) cudaFreeHost(c.res_host);
+    if (c.hpub) cudaFreeHost(c.hpub);
   }
   for (Buf *b : {&p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out}) cudaFree(b->p);
   if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
@@ -1205,9 +1235,7 @@ static int do_walk(kex_program *p, uint32_t start_state, cudaStream_t st) {
   if (p->timing) CK(cudaEventRecord(p->ev[3], st));
   k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->c->fail.p, nchunks, (RunResult *)p->c->res_dev.p);
   p->launches++;
-  CK(cudaMemcpyAsync(p->c->res_host, p->c->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return KEX_OK;
+  return fetch_sync(p, p->c->res_host, p->c->res_dev.p, sizeof(RunResult), st);
 }
 
 // fate maps of the first `nchunks_eff` chunks -> composed fate map (host, R bytes)
@@ -1398,9 +1426,7 @@ static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st) {
   k_reduce_fail<<<1, 1024, 0, st>>>((const uint32_t *)p->c->fail.p, nchunks, (RunResult *)p->c->res_dev.p);
   p->launches++;
   }
-  CK(cudaMemcpyAsync(p->c->res_host, p->c->res_dev.p, sizeof(RunResult), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return KEX_OK;
+  return fetch_sync(p, p->c->res_host, p->c->res_dev.p, sizeof(RunResult), st);
 }
 
 // backward up-sweep over the first nchunks_eff chunk maps; returns the level count
@@ -1488,8 +1514,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     p->launches++;
     if (p->timing) CK(cudaEventRecord(p->ev[5], st));
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(p->c->ctl_host, p->c->ctl.p, sizeof(FastCtl), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if ((rc = fetch_sync(p, p->c->ctl_host, p->c->ctl.p, sizeof(FastCtl), st))) return rc;
     if (p->c->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
     const size_t total = (size_t)p->c->ctl_host->total_out;
     *out_len = total;
@@ -1607,9 +1632,7 @@ static int shard_walk_seam(kex_program *p, uint32_t start_state, uint32_t *end_s
   size_t cnt[8];
   int nl = 0;
   if ((rc = lam_up(p, nchunks_eff, cnt, &nl, st))) return rc;
-  CK(cudaMemcpyAsync(h_seam, p->c->bmaps[nl - 1].p, nseam, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return KEX_OK;
+  return fetch_sync(p, h_seam, p->c->bmaps[nl - 1].p, nseam, st);
 }
 
 extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *end_state, size_t *fail_pos,
@@ -1774,7 +1797,25 @@ static int run_host_pipelined(kex_program *p, const uint8_t *h_in, size_t n, uin
     CK(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
   }
-  const size_t nw = (n + wave - 1) / wave;
+  // sub-wave boundaries: a quarter and a half wave first and last, so that the first kernel starts
+  // after a short copy and the last copy out is short (pipeline fill and drain)
+  std::vector<size_t> cut;
+  {
+    const size_t q = (wave / 4) & ~(size_t)4095, h = (wave / 2) & ~(size_t)4095;
+    size_t pos = 0;
+    cut.push_back(0);
+    const bool taper = q >= (1u << 20) && n >= 6 * wave;
+    if (taper) { cut.push_back(pos += q); cut.push_back(pos += h); }
+    const size_t tail = taper ? q + h : 0;
+    while (n - pos > wave + tail) cut.push_back(pos += wave);
+    if (taper) {
+      const size_t mid = (n - q - h) & ~(size_t)4095;      // sub-waves start 4096-aligned
+      if (mid > pos) cut.push_back(pos = mid);
+      cut.push_back(pos += h);
+    }
+    cut.push_back(n);
+  }
+  const size_t nw = cut.size() - 1;
   while (p->pipe_ev.size() < 2 * nw) {
     cudaEvent_t e;
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1782,7 +1823,7 @@ static int run_host_pipelined(kex_program *p, const uint8_t *h_in, size_t n, uin
   }
   uint8_t *d_in = (uint8_t *)p->hostio_in.p, *d_out = (uint8_t *)p->hostio_out.p;
   for (size_t i = 0; i < nw; ++i) {
-    const size_t off = i * wave, len = (n - off < wave) ? (n - off) : wave;
+    const size_t off = cut[i], len = cut[i + 1] - cut[i];
     CK(cudaMemcpyAsync(d_in + off, h_in + off, len, cudaMemcpyHostToDevice, p->s_h2d));
     CK(cudaEventRecord(p->pipe_ev[2 * i], p->s_h2d));
   }
@@ -1815,13 +1856,12 @@ static int run_host_pipelined(kex_program *p, const uint8_t *h_in, size_t n, uin
     return KEX_OK;
   };
   for (size_t i = 0; i < nw && rc == KEX_OK && !gave_up && !failed; ++i) {
-    const size_t off = i * wave, len = (n - off < wave) ? (n - off) : wave;
+    const size_t off = cut[i], len = cut[i + 1] - cut[i];
     p->c = &p->cx[i & 1];
     CK(cudaStreamWaitEvent(st, p->pipe_ev[2 * i], 0));
     p->launches = 0;
     if ((rc = do_summarize(p, 0, d_in + off, len, st))) break;
-    CK(cudaMemcpyAsync(map.data(), p->c->maps[p->c->nlevels - 1].p, Q1 * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if ((rc = fetch_sync(p, map.data(), p->c->maps[p->c->nlevels - 1].p, Q1 * sizeof(uint16_t), st))) break;
     uint32_t end_state = 0;
     size_t fpos = (size_t)-1;
     if ((rc = shard_walk_seam(p, state, &end_state, &fpos, seam.data(), st))) break;
@@ -1897,7 +1937,7 @@ extern "C" int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n, uint8
   int rc;
   if ((rc = ensure(p, p->hostio_in, n + 16))) return rc;
   if ((rc = ensure(p, p->hostio_out, out_cap + 16))) return rc;
-  size_t wave = 128u << 20;
+  size_t wave = 64u << 20;
   if (const char *e = getenv("KEX_HOST_WAVE_MIB")) { const long x = atol(e); if (x > 0) wave = (size_t)x << 20; }
   if (p->phases.size() == 1 && p->phases[0].v3.ok && n >= 2 * wave && !getenv("KEX_NO_HOST_PIPELINE")) {   // (a selected phase of a 1-phase program is that phase)
     rc = run_host_pipelined(p, h_in, n, h_out, out_cap, out_len, status, fail_count, wave);

@@ -152,6 +152,11 @@ def test_host_pipeline(name, monkeypatch):
     assert ei.value.code == -3
     monkeypatch.setenv("KEX_NO_HOST_PIPELINE", "1")
     _check(prog, ssts, d)
+    # tapered schedule (quarter and half sub-waves first and last) needs >= 6 sub-waves of >= 4 MiB
+    monkeypatch.delenv("KEX_NO_HOST_PIPELINE")
+    monkeypatch.setenv("KEX_HOST_WAVE_MIB", "4")
+    big = workloads.GENERATORS[name](27 << 20, seed=42).tobytes()
+    _check(prog, ssts, big[:len(big) - 12345])
 
 
 def test_pipeline_program():
