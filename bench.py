@@ -24,9 +24,9 @@ PROGRAM = "csv2json"
 OUT_PER_IN = 1.954            # +127 B per ~133 B row
 ALGO_BYTES_PER_IN = 1.0 + OUT_PER_IN
 # dram__bytes_read.sum + dram__bytes_write.sum of one k3_emit launch from the
-# committed `ncu --set full` capture (profiles/r01_ncu_v3_full_16gib.txt: 19.287 GB
-# read + 33.383 GB written for 17.180 GB of input), per input byte of that launch.
-EMIT_TRAFFIC_PER_IN = (19.286725 + 33.382569) / 17.179869
+# committed `ncu --set full` capture (profiles/r01_ncu_v3_full_16gib.txt: 19.557 GB
+# read + 33.385 GB written for 17.180 GB of input), per input byte of that launch.
+EMIT_TRAFFIC_PER_IN = (19.557043 + 33.384793) / 17.179869
 
 
 def peaks():
