@@ -41,6 +41,8 @@ struct V3Dev {
   uint32_t pool_stride;
   uint32_t NE;                 // NL * A emission entries
   const uint32_t *be3;         // [NE]  len | T << 15 | S << 16 | (lam_before * A) << 24;  S: emits exactly the input byte
+  const uint32_t *be3w;        // [NE]  write-pass copy (has_lit): a one-byte ASCII literal sits in bits 8-14 instead of a template
+  uint32_t has_lit;
   const uint32_t *tpl2;        // [NE]  pool offset | length << 16 | (hole offset + 1) << 24   (entries with T)
   // forward pass
   uint32_t pair;               // 1: fwdtab is the pair table [NM][C*C], 0: [NM][C]
@@ -425,7 +427,7 @@ __device__ __forceinline__ void v3_count(uint32_t pbe, const uint32_t (&ap)[8], 
   }
 }
 
-template <int LOG>
+template <int LOG, bool LIT>
 __device__ __forceinline__ void v3_wstep(uint32_t pbe, uint32_t &EL, uint32_t apw, uint32_t w, int k, uint32_t &o,
                                          uint32_t &recp) {
   const uint32_t addr = v3_be_addr<LOG>(pbe, EL, apw, k);
@@ -433,6 +435,7 @@ __device__ __forceinline__ void v3_wstep(uint32_t pbe, uint32_t &EL, uint32_t ap
   o = sub_byte0(EL, o);
   const uint32_t b = k == 0 ? w : byte_prmt(w, k);
   if (EL & 0x10000u) sts_u8(swz(o), b);
+  if (LIT && (EL & 0x7F00u)) sts_u8(swz(o), (EL >> 8) & 0x7Fu);      // one-byte literal: no template record
   if (EL & 0x8000u) {
     // staging address (18 bits) | entry address / 4 << 18; the input byte, for a template with a hole
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(recp), "r"(o + (addr << 16)), "r"(b) : "memory");
@@ -440,13 +443,13 @@ __device__ __forceinline__ void v3_wstep(uint32_t pbe, uint32_t &EL, uint32_t ap
   }
 }
 
-template <int LOG>
+template <int LOG, bool LIT>
 __device__ __forceinline__ void v3_write(uint32_t pbe, const uint32_t (&ap)[8], const uint32_t (&w)[8], uint32_t ELA,
                                          uint32_t ELB, uint32_t oA, uint32_t oB, uint32_t recpA, uint32_t recpB) {
 #pragma unroll
   for (int j = 15; j >= 0; --j) {
-    v3_wstep<LOG>(pbe, ELA, ap[j >> 2], w[j >> 2], j & 3, oA, recpA);
-    v3_wstep<LOG>(pbe, ELB, ap[4 + (j >> 2)], w[4 + (j >> 2)], j & 3, oB, recpB);
+    v3_wstep<LOG, LIT>(pbe, ELA, ap[j >> 2], w[j >> 2], j & 3, oA, recpA);
+    v3_wstep<LOG, LIT>(pbe, ELB, ap[4 + (j >> 2)], w[4 + (j >> 2)], j & 3, oB, recpB);
   }
 }
 
@@ -508,7 +511,7 @@ __device__ __forceinline__ void v3_stage_out(uint32_t stage_abs, uint32_t total,
   }
 }
 
-template <int LOG, bool REGS>
+template <int LOG, bool REGS, bool LIT>
 __global__ void __launch_bounds__(1024, 1)
 k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
         const uint16_t *__restrict__ samples, const uint16_t *__restrict__ blockpre,
@@ -524,7 +527,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
 
   // ---- tables (once per CTA)
   const uint32_t mulB_abs = base + V.o_mulB, trans_abs = base + V.o_trans, be_abs = base + V.o_BE;
-  if ((mulB_abs & 255u) || ((base + V.o_cls) & 255u) || be_abs + V.NE * STRIDE > 65536u) __trap();
+  if ((mulB_abs & 255u) || ((base + V.o_cls) & 255u) || be_abs + (LIT ? 2u : 1u) * V.NE * STRIDE > 65536u) __trap();
   // A row of the backward-element table is 256 bytes and holds `mcopies` copies of
   // its NG entries, (1 << mshift) bytes apart; lane l uses copy l % mcopies (the
   // copy offset is baked into byte 1 of its transition entries), so lanes in
@@ -548,6 +551,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
   for (uint32_t i = tid; i < V.NE * REP; i += blockDim.x) {
     const uint32_t ent = i / REP, s = i - ent * REP;
     *(uint32_t *)(smem_v3 + V.o_BE + ent * STRIDE + s * 4u) = V.be3[ent];
+    if (LIT) *(uint32_t *)(smem_v3 + V.o_BE + (V.NE + ent) * STRIDE + s * 4u) = V.be3w[ent];
   }
   for (uint32_t i = tid; i < 256; i += blockDim.x) smem_v3[V.o_cls + i] = P.cls[i];
   for (uint32_t i = tid; i < Q1; i += blockDim.x) smem_v3[V.o_guess + i] = 0xFFu;
@@ -562,6 +566,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
 
   const uint32_t cls_abs = base + V.o_cls, pool_abs = base + V.o_pool, tpl2_abs = base + V.o_tpl2;
   const uint32_t pbe = be_abs + slot4;
+  const uint32_t bew_abs = be_abs + (LIT ? V.NE * STRIDE : 0u), pbw = bew_abs + slot4;     // write-pass copy of the emission table
   const uint32_t wreg = V.o_warp + warp * warp_bytes;            // this warp's staging window, then its records
   const uint32_t stage_abs = base + wreg;
   const uint32_t recs_abs = stage_abs + stage_bytes + 128u;    // window + one row of slack, both multiples of 128 (swizzle)
@@ -795,12 +800,12 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       // does not need the global offset), one record per template
       const uint32_t oB = stage_abs + o_end, oA = oB - cntB;
       const uint32_t recpA = recs_abs + 8u * rec_excl, recpB = recpA + 8u * nrA;
-      v3_write<LOG>(pbe, ap, w, ELA, ELB, oA, oB, recpA, recpB);
+      v3_write<LOG, LIT>(pbw, ap, w, ELA, ELB, oA, oB, recpA, recpB);
       __syncwarp();
       // ---- templates: one lane per record
       for (uint32_t r = lane; r < total_recs; r += 32u) {
         const uint32_t rc = lds_u32_v(recs_abs + 8u * r), rb = lds_u32_v(recs_abs + 8u * r + 4u);
-        const uint32_t ent = (((rc >> 18) << 2) - be_abs) >> LOG;
+        const uint32_t ent = (((rc >> 18) << 2) - bew_abs) >> LOG;
         v3_copy_template(pool_abs, V.pool_stride, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
       }
       __syncwarp();
@@ -823,12 +828,13 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       uint32_t o = o_end, EL = ELB;
       for (int j = 31; j >= 0; --j) {
         const uint32_t a = lds_u8_v(sp + 32u + (uint32_t)j), b = lds_u8_v(sp + (uint32_t)j);
-        const uint32_t addr = (pbe + (a << LOG)) + (EL >> (24 - LOG));
+        const uint32_t addr = (pbw + (a << LOG)) + (EL >> (24 - LOG));
         EL = lds_u32(addr);
         o -= EL & 0xFFu;
         if (EL & 0x10000u) g[o] = (uint8_t)b;
+        if (LIT && (EL & 0x7F00u)) g[o] = (uint8_t)((EL >> 8) & 0x7Fu);
         if (EL & 0x8000u) {
-          const uint32_t t = lds_u32(tpl2_abs + 4u * ((addr - slot4 - be_abs) >> LOG));
+          const uint32_t t = lds_u32(tpl2_abs + 4u * ((addr - slot4 - bew_abs) >> LOG));
           const uint32_t src = t & 0xFFFFu, tl = (t >> 16) & 0xFFu, hole = t >> 24;
           for (uint32_t k = 0; k < tl; ++k) g[o + k] = (k + 1u == hole) ? (uint8_t)b : (uint8_t)lds_u8(pool_abs + src + k);
         }

@@ -749,7 +749,7 @@ static uint32_t rd32(const uint8_t *b, size_t off) {
 // Derived tables of the warp-autonomous kernels (kex_v3.cuh).  Programs whose
 // tables exceed the kernels' packed fields stay on the kex_fast.cuh kernels.
 static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const uint16_t *applyF, const uint32_t *BE,
-                   const uint32_t *tplinfo, uint32_t NM) {
+                   const uint32_t *tplinfo, const uint8_t *poolbytes, uint32_t NM) {
   V3Dev &v = ph.v3;
   memset(&v, 0, sizeof(v));
   if (getenv("KEX_NO_V3")) return KEX_OK;
@@ -757,11 +757,12 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
   const uint32_t Q1 = ph.dev.Q + 1, C = ph.dev.C, A = ph.dev.A, NL = F.NL, NB = F.NB, NE = NL * A;
   if ((NL - 1) * A > 255 || NB > 64 || F.NG > 127) return KEX_OK;
   // emission entries
-  std::vector<uint32_t> be3(NE), tpl2(NE, 0);
+  std::vector<uint32_t> be3(NE), be3w(NE), tpl2(NE, 0);
+  bool has_lit = false;
   for (uint32_t i = 0; i < NE; ++i) {
     const uint32_t e = BE[i];
     const uint32_t lamA = (e & 0xFFFCu) / 4u, len = (e >> 16) & 0xFFu;      // lam_before * A
-    uint32_t S = 0, T = 0;
+    uint32_t S = 0, T = 0, lit = 0;
     if (e & 1u) {
       S = 1;
     } else if (e & 2u) {
@@ -769,26 +770,43 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
       if (hm & (hm - 1u)) return KEX_OK;              // more than one hole
       uint32_t hole = 0;
       while (hm >> hole) ++hole;                      // hole offset + 1, 0 = none
-      T = 1;
-      tpl2[i] = src | (len << 16) | (hole << 24);
+      if (len == 1 && hole == 0 && poolbytes[src] >= 1 && poolbytes[src] < 0x80) {
+        lit = poolbytes[src];                         // a one-byte ASCII literal is stored by the write pass itself
+        has_lit = true;
+      } else {
+        T = 1;
+        tpl2[i] = src | (len << 16) | (hole << 24);
+      }
     }
     be3[i] = len | (T << 15) | (S << 16) | (lamA << 24);
+    be3w[i] = be3[i] | (lit << 8);
+  }
+  if (getenv("KEX_V3_NOLIT") && has_lit) {              // test knob: one-byte literals as ordinary templates
+    has_lit = false;
+    for (uint32_t i = 0; i < NE; ++i)
+      if (be3w[i] & 0x7F00u) {
+        const uint32_t e = BE[i], t = e >> 24;
+        be3[i] |= 0x8000u;
+        tpl2[i] = (tplinfo[2 * t] & 0xFFFFu) | (1u << 16);
+      }
+    be3w = be3;
   }
   // replicated tables must be addressable with 16 bits (2 KiB allowance for the window base)
   uint32_t log = 0;
   for (uint32_t cand : {7u, 5u}) {
-    const size_t end = (((size_t)NB * 256 + 127) & ~(size_t)127) + ((size_t)Q1 * C + NE) * (1u << cand);
+    const size_t end = (((size_t)NB * 256 + 127) & ~(size_t)127) + ((size_t)Q1 * C + (has_lit ? 2 : 1) * (size_t)NE) * (1u << cand);
     if (end + 2048 <= 65536) { log = cand; break; }
   }
   if (!log) return KEX_OK;
   const uint32_t stride = 1u << log;
   v.log = log;
   v.NE = NE;
+  v.has_lit = has_lit ? 1u : 0u;
   uint32_t sp = 0;
   v.o_mulB = sp; sp += NB * 256u;
   sp = (sp + 127u) & ~127u;
   v.o_trans = sp; sp += Q1 * C * stride;
-  v.o_BE = sp; sp += NE * stride;
+  v.o_BE = sp; sp += (has_lit ? 2u : 1u) * NE * stride;
   sp = (sp + 255u) & ~255u;
   v.o_cls = sp; sp += 256;
   v.o_compB = sp; sp += NB * NB;
@@ -842,20 +860,26 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
       }
   }
   v.NM = NM;
-  const size_t o_be = 0, o_tp = o_be + 4ull * NE, o_fw = (o_tp + 4ull * NE + 15) & ~(size_t)15,
+  const size_t o_be = 0, o_bw = o_be + 4ull * NE, o_tp = o_bw + 4ull * NE, o_fw = (o_tp + 4ull * NE + 15) & ~(size_t)15,
                o_cp = (o_fw + fwd.size() * 2 + 15) & ~(size_t)15, tot = o_cp + comp.size() * 2;
   std::vector<uint8_t> img(tot, 0);
   memcpy(img.data() + o_be, be3.data(), 4ull * NE);
+  memcpy(img.data() + o_bw, be3w.data(), 4ull * NE);
   memcpy(img.data() + o_tp, tpl2.data(), 4ull * NE);
   memcpy(img.data() + o_fw, fwd.data(), fwd.size() * 2);
   memcpy(img.data() + o_cp, comp.data(), comp.size() * 2);
   CK(cudaMalloc(&ph.d_v3, tot));
   CK(cudaMemcpy(ph.d_v3, img.data(), tot, cudaMemcpyHostToDevice));
   v.be3 = (const uint32_t *)((const uint8_t *)ph.d_v3 + o_be);
+  v.be3w = (const uint32_t *)((const uint8_t *)ph.d_v3 + o_bw);
   v.tpl2 = (const uint32_t *)((const uint8_t *)ph.d_v3 + o_tp);
   v.fwdtab = (const uint16_t *)((const uint8_t *)ph.d_v3 + o_fw);
   v.compF = (const uint16_t *)((const uint8_t *)ph.d_v3 + o_cp);
   v.ok = 1;
+  if (getenv("KEX_DEBUG"))
+    fprintf(stderr, "kexcuda: v3 kernels: entry stride %u B, %u emission entries, one-byte literals %s, forward table %s (%u entries), "
+                    "%u forward elements, tables %u B\n", stride, NE, has_lit ? "direct" : "none", pair ? "pairs" : "single",
+            v.fwd_entries, NM, v.o_warp);
   return KEX_OK;
 }
 
@@ -925,7 +949,7 @@ static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph
   d.pool = db + off[10];
   ph.smem_ef_tables = tables;
   ph.fast = true;
-  return load_v3(p, ph, mulF, applyF, BE, tplinfo, NM);
+  return load_v3(p, ph, mulF, applyF, BE, tplinfo, f + off[10], NM);
 }
 
 static int load_phase(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
@@ -1045,10 +1069,11 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
   cudaFuncSetAttribute(k3_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k3_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k3_seams, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-  cudaFuncSetAttribute(k3_emit<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
-  cudaFuncSetAttribute(k3_emit<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
-  cudaFuncSetAttribute(k3_emit<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
-  cudaFuncSetAttribute(k3_emit<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+#define V3_EACH(X) X(7, true, true) X(7, true, false) X(7, false, true) X(7, false, false) \
+                   X(5, true, true) X(5, true, false) X(5, false, true) X(5, false, false)
+#define V3_ATTR(L, R, T) cudaFuncSetAttribute(k3_emit<L, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  V3_EACH(V3_ATTR)
+#undef V3_ATTR
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
   for (Ctx &c : p->cx) {
     if (cudaMallocHost((void **)&c.ctl_host, sizeof(FastCtl)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
@@ -1491,25 +1516,25 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     const size_t smem3 = (size_t)V.o_warp + (size_t)nwork * warp_bytes;
     const uint32_t nwarp = nwork + 1u;
     int occ = 0;
-    if (V.log == 7) {
-      if (NL > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<7, true>, (int)(nwarp * 32u), smem3));
-      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<7, false>, (int)(nwarp * 32u), smem3));
-    } else {
-      if (NL > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<5, true>, (int)(nwarp * 32u), smem3));
-      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<5, false>, (int)(nwarp * 32u), smem3));
-    }
+    const bool regs = NL > 1, lit = V.has_lit != 0;
+#define V3_OCC(L, R, T)                                                                                              \
+    if (V.log == L && regs == R && lit == T)                                                                        \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_emit<L, R, T>, (int)(nwarp * 32u), smem3));
+    V3_EACH(V3_OCC)
+#undef V3_OCC
     if (occ < 1) return KEX_ERR_UNSUPPORTED;
     const size_t ngroups = (ntiles + nwork - 1) / nwork;
     size_t ctas = ngroups;
     if (ctas > (size_t)occ * (size_t)p->num_sms) ctas = (size_t)occ * (size_t)p->num_sms;
     if (p->timing) CK(cudaEventRecord(p->ev[4], st));
-#define V3_LAUNCH(LOGV, REGSV)                                                                                      \
-    k3_emit<LOGV, REGSV><<<(unsigned)ctas, nwarp * 32u, smem3, st>>>(                                               \
-        P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,                           \
-        (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p, (unsigned long long *)p->c->desc.p,           \
-        (FastCtl *)p->c->ctl.p, d_out, out_cap, (unsigned long long)p->emit_out_off, ph.v3_stage, warp_bytes, ph.v3_reccap, nospec)
-    if (V.log == 7) { if (NL > 1) V3_LAUNCH(7, true); else V3_LAUNCH(7, false); }
-    else { if (NL > 1) V3_LAUNCH(5, true); else V3_LAUNCH(5, false); }
+#define V3_LAUNCH(L, R, T)                                                                                          \
+    if (V.log == L && regs == R && lit == T)                                                                        \
+      k3_emit<L, R, T><<<(unsigned)ctas, nwarp * 32u, smem3, st>>>(                                                 \
+          P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,                   \
+          (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,  \
+          (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,                                \
+          (unsigned long long)p->emit_out_off, ph.v3_stage, warp_bytes, ph.v3_reccap, nospec);
+    V3_EACH(V3_LAUNCH)
 #undef V3_LAUNCH
     p->launches++;
     if (p->timing) CK(cudaEventRecord(p->ev[5], st));

@@ -248,7 +248,7 @@ def test_large_properties_tiled(name, block_mib, reps):
 
 @pytest.mark.parametrize("name", PROGS)
 @pytest.mark.parametrize("knob", [{"KEX_V3_NOSPEC": "1"}, {"KEX_V3_STAGE": "2048", "KEX_V3_RECCAP": "8"},
-                                  {"KEX_NO_V3": "1"}])
+                                  {"KEX_V3_NOLIT": "1"}, {"KEX_NO_V3": "1"}])
 def test_v3_paths_forced(name, knob, monkeypatch):
     """The rarely taken paths of the v3 kernels, forced: exact live sets for
     every tile (no guessing), tiles that do not fit the staging window / record
@@ -264,3 +264,23 @@ def test_v3_paths_forced(name, knob, monkeypatch):
     _check(prog, ssts, d)
     _check(prog, ssts, d[:700001])
     _check(prog, ssts, d[:1000000] + b"\x01" + d[1000001:])
+
+
+@pytest.mark.parametrize("nolit", [False, True])
+def test_one_byte_literals(nolit, monkeypatch):
+    """An action that replaces its input byte by a different one-byte literal:
+    the write pass of k3_emit stores it directly (no template record); with
+    KEX_V3_NOLIT the same emission goes through a template record."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    if nolit:
+        monkeypatch.setenv("KEX_V3_NOLIT", "1")
+    src = 'main := (~/a/ "x" | /b/ | ~/c/ "yz" | /\\n/)*\n'
+    prog = CompiledProgram(compile_kex(src))
+    ssts = build_ssts(src)
+    assert prog.info()["chunk_bytes"] == 1024
+    rng = np.random.default_rng(7)
+    d = bytes(rng.choice(np.frombuffer(b"aabbbc\n", dtype=np.uint8), size=1 << 20))
+    _check(prog, ssts, d)
+    _check(prog, ssts, d[:333333] + b"q" + d[333334:])
+    st, out, _ = prog.run(b"abcab\n")
+    assert (st, out) == (0, b"xbyzxb\n")
