@@ -408,10 +408,11 @@ __device__ __forceinline__ void v3_forward(uint32_t cls_abs, const uint32_t (&w)
 
 // Emission entry address of action a under the live set encoded in EL (byte 3
 // = lam * A; bits 24-LOG .. 23 are zero, so EL >> (24-LOG) = (lam * A) << LOG).
+// (one IDP.4A on the fma pipe extracts action byte k, scales it by the entry
+// stride and adds the table base; the alu pipe is the busier one in these passes)
 template <int LOG>
 __device__ __forceinline__ uint32_t v3_be_addr(uint32_t pbe, uint32_t EL, uint32_t apw, int k) {
-  const uint32_t a = byte_prmt(apw, k);
-  return (pbe + (a << LOG)) + (EL >> (24 - LOG));
+  return __dp4a(apw, (1u << LOG) << (8 * k), pbe) + (EL >> (24 - LOG));
 }
 
 // count pass over both halves: byte length in the low 14 bits, records above
@@ -433,7 +434,7 @@ __device__ __forceinline__ void v3_wstep(uint32_t pbe, uint32_t &EL, uint32_t ap
   const uint32_t addr = v3_be_addr<LOG>(pbe, EL, apw, k);
   EL = lds_u32(addr);
   o = sub_byte0(EL, o);
-  const uint32_t b = k == 0 ? w : byte_prmt(w, k);
+  const uint32_t b = k == 0 ? w : __umulhi(w, 1u << (32 - 8 * k));     // w >> 8k on the fma pipe; the store takes the low byte
   if (EL & 0x10000u) sts_u8(swz(o), b);
   if (LIT && (EL & 0x7F00u)) sts_u8(swz(o), (EL >> 8) & 0x7Fu);      // one-byte literal: no template record
   if (EL & 0x8000u) {
