@@ -284,3 +284,66 @@ def test_one_byte_literals(nolit, monkeypatch):
     _check(prog, ssts, d[:333333] + b"q" + d[333334:])
     st, out, _ = prog.run(b"abcab\n")
     assert (st, out) == (0, b"xbyzxb\n")
+
+
+def _random_program(rng):
+    """A small well-formed Kleenex program: a starred choice of terms built from
+    byte classes over {a..e, newline}, suppression, output literals and
+    bounded repetition (ordered choice makes overlapping alternatives legal)."""
+    atoms = ["/a/", "/b/", "/[ab]/", "/[c-e]/", "/[a-e]/", "/\\n/", "/ab/", "/a+/", "/[bc]*d/", "/e{2,3}/"]
+    lits = ['"x"', '"yz"', '"<"', '">\\n"', '"--"', '"0123456789"']
+
+    def term(depth):
+        k = rng.integers(0, 7)
+        if k == 0:
+            return atoms[rng.integers(len(atoms))]
+        if k == 1:
+            return "~" + atoms[rng.integers(len(atoms))]
+        if k == 2:
+            return lits[rng.integers(len(lits))] + " " + atoms[rng.integers(len(atoms))]
+        if k == 3:
+            return atoms[rng.integers(len(atoms))] + " " + lits[rng.integers(len(lits))]
+        if k == 4 and depth < 2:
+            return "(" + term(depth + 1) + " | " + term(depth + 1) + ")"
+        if k == 5 and depth < 2:
+            return "(" + term(depth + 1) + " " + term(depth + 1) + ")"
+        return "~" + atoms[rng.integers(len(atoms))] + " " + lits[rng.integers(len(lits))]
+
+    n = int(rng.integers(2, 5))
+    return "main := (" + " | ".join(term(0) for _ in range(n)) + ")*\n"
+
+
+def test_random_programs_vs_oracle():
+    """Seeded random programs x random inputs (accepting prefixes and rejects):
+    exercises table construction, kernel selection and every kernel family on
+    shapes the bundled programs do not have."""
+    from kleenexlang_b200.runtime import CompiledProgram, KexError
+    rng = np.random.default_rng(20261017)
+    alphabet = np.frombuffer(b"aaabbbcde\n", dtype=np.uint8)
+    done = accepted = 0
+    for _ in range(60):
+        src = _random_program(rng)
+        try:
+            ssts = build_ssts(src)
+            blob = compile_kex(src)
+        except Exception:
+            continue                                   # not well-formed / exceeds a front-end limit
+        try:
+            prog = CompiledProgram(blob)
+        except KexError:
+            continue
+        for n in (0, 1, 37, 5000, 70001):
+            d = bytes(rng.choice(alphabet, size=n))
+            got, exp = prog.run(d), oracle_run(ssts, d)
+            assert got[:2] == exp[:2] and (got[0] == 0 or got[2] == exp[2]), (src, n)
+            if exp[0]:
+                # the consumed prefix, tiled: mostly accepting runs with real output
+                pre = d[:exp[2]]
+                if pre:
+                    big = pre * max(1, 40000 // len(pre))
+                    got, exp = prog.run(big), oracle_run(ssts, big)
+                    assert got[:2] == exp[:2] and (got[0] == 0 or got[2] == exp[2]), (src, n, "tiled prefix")
+                    accepted += exp[0] == 0
+        done += 1
+        prog.close()
+    assert done >= 20 and accepted >= 20
