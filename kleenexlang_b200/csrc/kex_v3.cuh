@@ -512,6 +512,15 @@ __device__ __forceinline__ void v3_stage_out(uint32_t stage_abs, uint32_t total,
   }
 }
 
+// programs whose emissions are at most three bytes long: no word path
+__device__ __forceinline__ void v3_copy_short(uint32_t pool_abs, uint32_t o, uint32_t t, uint32_t byte) {
+  const uint32_t ps = pool_abs + (t & 0xFFFFu), len = (t >> 16) & 0xFFu;
+#pragma unroll
+  for (uint32_t k = 0; k < 3; ++k)
+    if (k < len) sts_u8(swz(o + k), lds_u8(ps + k));
+  if (t >> 24) sts_u8(swz(o + (t >> 24) - 1u), byte);
+}
+
 template <int LOG, bool REGS, bool LIT>
 __global__ void __launch_bounds__(1024, 1)
 k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
@@ -807,7 +816,8 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       for (uint32_t r = lane; r < total_recs; r += 32u) {
         const uint32_t rc = lds_u32_v(recs_abs + 8u * r), rb = lds_u32_v(recs_abs + 8u * r + 4u);
         const uint32_t ent = (((rc >> 18) << 2) - bew_abs) >> LOG;
-        v3_copy_template(pool_abs, V.pool_stride, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
+        if (F.max_emit <= 3u) v3_copy_short(pool_abs, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
+        else v3_copy_template(pool_abs, V.pool_stride, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
       }
       __syncwarp();
       prev_total = total;                                          // staged out after the next tile's count
