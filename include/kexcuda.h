@@ -74,7 +74,10 @@ int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n,
 
 /* Same, with host buffers: host->device copy of the input, the run, and a
  * device->host copy of the output all happen inside the call
- * (the stdin/stdout role of crt/crt.c:293-312,107-136). */
+ * (the stdin/stdout role of crt/crt.c:293-312,107-136).  Large inputs of
+ * single-phase programs are cut into sub-waves that are copied in, evaluated
+ * as consecutive shards of one run and copied out on three streams; pinned
+ * host buffers make the copies asynchronous, pageable ones work too. */
 int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n,
                  uint8_t *h_out, size_t out_cap, size_t *out_len,
                  int *status, size_t *fail_count);

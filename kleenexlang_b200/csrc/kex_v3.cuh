@@ -4,26 +4,36 @@
 // the tile that creates a byte writes it), re-laid for the B200 SM:
 //
 //   k3_fwd     state chain of `matchN` (src/KMC/Program/Backends/C.hs:72-83)
-//              for all start states at once.  One thread walks two 4 KiB
-//              chunks interleaved (two independent dependent-load chains), two
-//              input bytes per table lookup (pair table: row offset of the
-//              product element), prefix element sampled every 16 bytes.
+//              for all start states at once.  One warp walks a pair of 4 KiB
+//              chunks, lane = one 128-byte block of each (two independent
+//              dependent-load chains, every warp load inside one contiguous
+//              4 KiB region), two input bytes per table lookup (pair table: row
+//              offset of the product element), prefix element sampled every 16
+//              bytes relative to the block; the blocks' elements are composed
+//              across the warp through the element composition table.
 //   k3_seams   per 1 KiB tile from its true start state: backward (live-set)
 //              element until it is a constant map; exact position of a failing
 //              transition (C.hs:79-81) by atomicMin.
 //   k3_emit    outputconst/outputarray/output and the register buffers of
-//              crt/crt.c:161-283.  One WARP per 1 KiB tile, no CTA barriers:
-//              each lane owns 32 input bytes as two independent 16-byte halves
-//              (ILP 2 in every pass).  Transition and emission tables are
-//              replicated once per lane in shared memory (entry stride 128 B:
-//              lane l only ever touches bank l, so the per-byte lookups are
-//              bank-conflict free) and hold absolute shared addresses, so a
-//              step is LEA.HI + LDS.  Passes per byte: forward (action id,
-//              backward element), count (IDP.4A accumulates length and record
-//              count at once), write (input bytes to a per-warp staging window,
-//              one record per template), then templates are copied word-wise
-//              and the window leaves with one TMA bulk store.  Tile totals are
-//              chained with a decoupled look-back, one descriptor per tile.
+//              crt/crt.c:161-283.  One persistent CTA per SM = 31 worker warps
+//              + 1 scan warp, no CTA-wide barrier in the loop.  A worker owns a
+//              1 KiB tile; each lane owns 32 input bytes as two independent
+//              16-byte halves (ILP 2 in every pass).  Transition and emission
+//              tables are replicated once per lane in shared memory (entry
+//              stride 128 B: lane l only ever touches bank l, so the per-byte
+//              lookups are bank-conflict free) and hold absolute shared
+//              addresses.  Passes per byte: forward (action id [, backward
+//              element]), count (IDP.4A accumulates length and record count at
+//              once), write (input bytes into a swizzled per-warp staging
+//              window at tile-relative offsets, one record per template), then
+//              templates are copied word-wise.  The live set at the end of
+//              every half is guessed from the state there and verified by the
+//              count pass (exact re-evaluation on a miss).  The scan warp
+//              chains one descriptor per 31-tile group with a decoupled
+//              look-back and hands every worker its global offset, which the
+//              worker only needs for the stage-out -- deferred until after the
+//              next tile's count pass -- 16-byte stores aligned to the
+//              destination, source words funnel-shifted from the window.
 #pragma once
 
 #define V3_TILE 1024u
