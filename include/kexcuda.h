@@ -82,6 +82,29 @@ int kex_run_host(kex_program *p, const uint8_t *h_in, size_t n,
                  uint8_t *h_out, size_t out_cap, size_t *out_len,
                  int *status, size_t *fail_count);
 
+/* ---- block streaming ------------------------------------------------------
+ * Replaces the sliding input window and the flushed output window of the
+ * compiled binary (crt/crt.c:61,299-305 readnext; 107-136 buf_flush): the input
+ * is fed block by block and never has to be resident as a whole.
+ *   kex_stream_begin : start a run
+ *   kex_stream_feed  : feed the next input block (host memory); writes to h_out
+ *                      the output of the PREVIOUS block (it needs one block of
+ *                      lookahead), *out_len = 0 on the first call
+ *   kex_stream_end   : output of the last block and of the end-of-input action,
+ *                      status and count of the whole run.  On KEX_REJECT the
+ *                      caller keeps only whole 16 KiB flushes of the
+ *                      concatenated stream, as the reference does.
+ * Single-phase programs on the v3 kernels.  A block whose seam summary is not
+ * a constant map (e.g. a short last block) keeps its predecessor waiting too;
+ * a third block in that situation gives KEX_ERR_UNSUPPORTED -- feed larger
+ * blocks or use kex_run_host.  KEX_ERR_OUT_CAP: *out_len = bytes needed; the call changed
+ * nothing, repeat it with a larger h_out (same block for kex_stream_feed). */
+int kex_stream_begin(kex_program *p);
+int kex_stream_feed(kex_program *p, const uint8_t *h_in, size_t n, uint8_t *h_out,
+                    size_t out_cap, size_t *out_len);
+int kex_stream_end(kex_program *p, uint8_t *h_out, size_t out_cap, size_t *out_len,
+                   int *status, size_t *fail_count);
+
 /* ---- sharded evaluation (one shard per GPU; single-phase programs) --------
  * The transducer run is a prefix computation over the SST's transition monoid
  * (src/KMC/SymbolicSST.hs:122-136): forward over the state maps, backward

@@ -697,6 +697,12 @@ struct kex_program {
   Ctx cx[2];
   Ctx *c = &cx[0];
   Buf inter[2], hostio_in, hostio_out;
+  // block streaming (kex_stream_*): two blocks resident, the older one waits for its seam code
+  Buf sin[2], sout;
+  bool st_open = false, st_failed = false;
+  uint32_t st_state = 0, st_blocks = 0, st_nq = 0;      // st_nq: blocks walked but not yet emitted (<= 2)
+  size_t st_q[2] = {0, 0}, st_consumed = 0, st_fail_at = 0;
+  std::vector<uint8_t> st_seam;                         // seam summary of the newest block when two wait
   int num_sms = 0;
   // host pipeline (kex_run_host)
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
@@ -1106,7 +1112,7 @@ extern "C" void kex_free(kex_program *p) {
     if (c.res_host) cudaFreeHost(c.res_host);
     if (c.hpub) cudaFreeHost(c.hpub);
   }
-  for (Buf *b : {&p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out}) cudaFree(b->p);
+  for (Buf *b : {&p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out, &p->sin[0], &p->sin[1], &p->sout}) cudaFree(b->p);
   if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
   if (p->s_comp) cudaStreamDestroy(p->s_comp);
   if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
@@ -1802,6 +1808,128 @@ extern "C" int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n, uin
     cudaEventElapsedTime(&p->ms[3], p->ev[6], p->ev[7]);
   }
   CK(cudaStreamSynchronize(st));
+  return KEX_OK;
+}
+
+// ------------------------------------------------------------ block streaming
+// stdin -> stdout with bounded memory (the role of the 2 x 16 KiB input window
+// and the 16 KiB output window of crt/crt.c:61,299-305,107-136): the caller
+// feeds blocks of the input in order; every block is evaluated as the next
+// shard of one run (state map -> true start state -> seam summary), and the
+// block before it is emitted once the new block's seam summary fixes the seam
+// code at its end.  Single-phase programs on the v3 kernels whose seam
+// summaries are constant maps (record-shaped programs).
+// Emit block `blk` (its scratch context is cx[blk & 1]) with the seam code at its end.
+static int stream_emit_block(kex_program *p, uint32_t blk, size_t n_eff, uint32_t code, uint8_t *h_out, size_t out_cap,
+                             size_t *out_len) {
+  p->c = &p->cx[blk & 1];
+  *out_len = 0;
+  // device buffer: a guess from the input size first, the exact size if that was too small
+  int rc = ensure(p, p->sout, 4 * n_eff + (1u << 20));
+  if (rc) return rc;
+  size_t ol = 0;
+  rc = do_emit(p, code, n_eff, (uint8_t *)p->sout.p, p->sout.cap - 16, &ol, nullptr);
+  if (rc == KEX_ERR_OUT_CAP) {
+    if ((rc = ensure(p, p->sout, ol + 16))) return rc;
+    rc = do_emit(p, code, n_eff, (uint8_t *)p->sout.p, p->sout.cap - 16, &ol, nullptr);
+  }
+  if (rc) { *out_len = ol; return rc; }
+  *out_len = ol;
+  if (ol > out_cap) return KEX_ERR_OUT_CAP;
+  if (ol) CK(cudaMemcpy(h_out, p->sout.p, ol, cudaMemcpyDeviceToHost));
+  return KEX_OK;
+}
+
+extern "C" int kex_stream_begin(kex_program *p) {
+  if (!p) return KEX_ERR_ARG;
+  if (p->phases.size() != 1 || !p->phases[0].v3.ok) return KEX_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(p->device));
+  p->st_open = true; p->st_failed = false;
+  p->st_state = p->phases[0].dev.init; p->st_blocks = 0; p->st_nq = 0;
+  p->st_consumed = 0; p->st_fail_at = 0;
+  return KEX_OK;
+}
+
+extern "C" int kex_stream_feed(kex_program *p, const uint8_t *h_in, size_t n, uint8_t *h_out, size_t out_cap,
+                               size_t *out_len) {
+  if (!p || !p->st_open || !out_len || !h_in || n == 0) return KEX_ERR_ARG;
+  CK(cudaSetDevice(p->device));
+  *out_len = 0;
+  if (p->st_failed) return KEX_OK;                       // input after the failure is ignored (C.hs:79-81)
+  if (p->st_nq == 2) return KEX_ERR_UNSUPPORTED;         // two blocks already wait for their seam codes
+  PhaseHost &ph = p->phases[0];
+  const uint32_t NL = ph.fdev.NL;
+  const uint32_t k = p->st_blocks;
+  Buf &in = p->sin[k & 1];
+  int rc = ensure(p, in, n + 16);
+  if (rc) return rc;
+  CK(cudaMemcpy(in.p, h_in, n, cudaMemcpyHostToDevice));
+  p->c = &p->cx[k & 1];
+  p->launches = 0;
+  if ((rc = do_summarize(p, 0, (const uint8_t *)in.p, n, nullptr))) return rc;
+  uint32_t end_state = 0;
+  size_t fpos = (size_t)-1;
+  std::vector<uint8_t> seam(NL);
+  if ((rc = shard_walk_seam(p, p->st_state, &end_state, &fpos, seam.data(), nullptr))) return rc;
+  const bool failed = fpos != (size_t)-1;
+  bool constant = true;
+  for (uint32_t l = 1; l < NL; ++l) constant = constant && seam[l] == seam[0];
+  if (p->st_nq == 1 && (constant || failed)) {
+    // this block fixes the seam code at the end of the block before it (after a failure nothing is live)
+    rc = stream_emit_block(p, k - 1, p->st_q[0], seam[0], h_out, out_cap, out_len);
+    p->c = &p->cx[0];
+    if (rc) return rc;                                   // nothing was committed: the call can be repeated
+    p->st_nq = 0;
+  } else if (p->st_nq == 1) {
+    p->st_seam = seam;                                   // resolved by kex_stream_end (e.g. a short last block)
+  }
+  p->st_q[p->st_nq++] = failed ? fpos : n;
+  p->st_blocks = k + 1;
+  if (failed) { p->st_failed = true; p->st_fail_at = p->st_consumed + fpos; }
+  p->st_consumed += n;
+  p->st_state = end_state;
+  p->c = &p->cx[0];
+  return KEX_OK;
+}
+
+extern "C" int kex_stream_end(kex_program *p, uint8_t *h_out, size_t out_cap, size_t *out_len, int *status,
+                              size_t *fail_count) {
+  if (!p || !p->st_open || !out_len || !status || !fail_count) return KEX_ERR_ARG;
+  CK(cudaSetDevice(p->device));
+  PhaseHost &ph = p->phases[0];
+  *out_len = 0;
+  const int32_t fa = p->st_failed ? -1 : ph.fin[p->st_state];
+  const bool accept = fa >= 0;
+  const uint32_t last_code = accept ? final_code(ph, p->st_state) : 0u;
+  size_t body = 0;
+  for (uint32_t i = 0; i < p->st_nq; ++i) {
+    const uint32_t blk = p->st_blocks - p->st_nq + i;
+    const uint32_t code = (i + 1 == p->st_nq) ? last_code : (uint32_t)p->st_seam[last_code];
+    size_t ol = 0;
+    int rc = stream_emit_block(p, blk, p->st_q[i], code, h_out + body, out_cap > body ? out_cap - body : 0, &ol);
+    p->c = &p->cx[0];
+    if (rc) { *out_len = body + ol + (rc == KEX_ERR_OUT_CAP ? (size_t)1 << 20 : 0); return rc; }
+    body += ol;
+  }
+  if (accept) {
+    const ActHdr &h = ph.acts[fa];
+    size_t o = body;
+    for (uint32_t k = 0; k < h.npieces; ++k) {
+      const Piece &pc = ph.pieces[h.piece_off + k];
+      if (o + pc.len > out_cap) { *out_len = o + ((size_t)1 << 20); return KEX_ERR_OUT_CAP; }
+      memcpy(h_out + o, ph.consts.data() + pc.off, pc.len);
+      o += pc.len;
+    }
+    *out_len = o;
+    *status = KEX_ACCEPT;
+    *fail_count = 0;
+  } else {
+    // the caller keeps only whole 16 KiB flushes of the whole stream (crt.c:140-159,217-227)
+    *out_len = body;
+    *status = KEX_REJECT;
+    *fail_count = p->st_failed ? p->st_fail_at : p->st_consumed;
+  }
+  p->st_open = false;
   return KEX_OK;
 }
 

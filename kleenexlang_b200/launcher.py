@@ -92,9 +92,33 @@ def main(blob_path, argv):
     cp = CompiledProgram(open(blob_path, "rb").read())
     if phase:
         cp.select_phase(phase)
-    data = sys.stdin.buffer.read()
-    status, out, count = cp.run(data)
-    sys.stdout.buffer.write(out)
+    # inputs larger than one block are streamed block by block with bounded memory
+    # (kex_stream_*); KEX_NO_STREAM=1 reads the whole input first
+    block = int(os.environ.get("KEX_STREAM_BLOCK_MIB", "256")) << 20
+    first = sys.stdin.buffer.read(block)
+    more = sys.stdin.buffer.read(1) if len(first) == block else b""
+    streamable = bool(more) and not phase and not os.environ.get("KEX_NO_STREAM")
+    if streamable:
+        from .runtime import KexError
+        try:
+            cp._check(cp._L.kex_stream_begin(cp._h))
+        except KexError:
+            streamable = False                  # multi-phase program or tables beyond the v3 kernels
+    if streamable:
+        def blocks():
+            yield first
+            head = more
+            while True:
+                blk = head + sys.stdin.buffer.read(block - len(head))
+                head = b""
+                if not blk:
+                    return
+                yield blk
+        status, count = cp.run_stream(blocks(), sys.stdout.buffer.write)
+    else:
+        data = first + more + (sys.stdin.buffer.read() if more else b"")
+        status, out, count = cp.run(data)
+        sys.stdout.buffer.write(out)
     sys.stdout.buffer.flush()
     if status != 0:
         sys.stderr.write("Match error at input symbol %d!\n" % count)

@@ -31,7 +31,7 @@ class KexInfo(ctypes.Structure):
 
 EXPORTS = ["kex_load", "kex_free", "kex_info", "kex_run_device", "kex_run_host", "kex_shard_summarize",
            "kex_seam_bytes", "kex_shard_walk", "kex_stitch_live", "kex_shard_emit", "kex_final_action", "kex_out_bound",
-           "kex_select_phase", "kex_last_launch_count",
+           "kex_select_phase", "kex_stream_begin", "kex_stream_feed", "kex_stream_end", "kex_last_launch_count",
            "kex_set_timing", "kex_last_kernel_ms", "kex_strerror", "kex_last_cuda_error"]
 
 
@@ -64,6 +64,9 @@ def lib():
     L.kex_final_action.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(u32),
                                    ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz)]
     L.kex_select_phase.argtypes = [vp, u32]
+    L.kex_stream_begin.argtypes = [vp]
+    L.kex_stream_feed.argtypes = [vp, ctypes.c_char_p, sz, u8p, sz, ctypes.POINTER(sz)]
+    L.kex_stream_end.argtypes = [vp, u8p, sz, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(sz)]
     L.kex_out_bound.argtypes = [vp, sz]
     L.kex_out_bound.restype = sz
     L.kex_last_launch_count.argtypes = [vp]
@@ -158,6 +161,49 @@ class CompiledProgram:
                 continue
             self._check(rc)
             return st.value, buf.raw[:ol.value], fc.value
+
+    def run_stream(self, blocks, write, block_out_cap=None):
+        """`./bin < in > out` with bounded memory: `blocks` yields the input in
+        order, `write(bytes)` receives the output.  Like the reference's
+        runtime only whole 16 KiB flushes are written until the run accepts
+        (crt/crt.c:107-159,217-227).  Returns (status, count)."""
+        L = self._L
+        self._check(L.kex_stream_begin(self._h))
+        ol, st, fc = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_size_t()
+        held = bytearray()
+
+        def push(chunk, final_accept=False):
+            held.extend(chunk)
+            keep = 0 if final_accept else len(held) % 16384
+            if len(held) > keep:
+                write(bytes(held[:len(held) - keep]))
+                del held[:len(held) - keep]
+
+        cap = block_out_cap or 4096
+        buf = ctypes.create_string_buffer(cap)
+
+        def call(fn):
+            # KEX_ERR_OUT_CAP leaves the stream untouched: repeat with the size it asks for
+            nonlocal cap, buf
+            while True:
+                rc = fn(ctypes.cast(buf, ctypes.c_void_p), cap)
+                if rc != KEX_ERR_OUT_CAP:
+                    self._check(rc)
+                    return
+                cap = ol.value + 4096
+                buf = ctypes.create_string_buffer(cap)
+
+        for blk in blocks:
+            if not blk:
+                continue
+            if not block_out_cap and cap < 3 * len(blk):
+                cap = 3 * len(blk)
+                buf = ctypes.create_string_buffer(cap)
+            call(lambda b, c: L.kex_stream_feed(self._h, blk, len(blk), b, c, ctypes.byref(ol)))
+            push(ctypes.string_at(buf, ol.value))
+        call(lambda b, c: L.kex_stream_end(self._h, b, c, ctypes.byref(ol), ctypes.byref(st), ctypes.byref(fc)))
+        push(ctypes.string_at(buf, ol.value), final_accept=st.value == ACCEPT)
+        return st.value, fc.value
 
     def run_device(self, d_in: int, n: int, d_out: int, out_cap: int, stream: int = 0):
         """Input and output are device pointers (ints).  Returns

@@ -347,3 +347,37 @@ def test_random_programs_vs_oracle():
         done += 1
         prog.close()
     assert done >= 20 and accepted >= 20
+
+
+@pytest.mark.parametrize("name", ["csv2json", "iso_datetime_to_json", "fastq2fasta", "thousand_sep"])
+def test_block_streaming(name):
+    """kex_stream_*: the input is fed in blocks (any sizes), each block's output
+    comes back one block later, whole 16 KiB flushes only until the run accepts;
+    equal to the whole-input run on accepting and rejecting inputs."""
+    prog, ssts = gpu_prog(program_source(name))
+    d = workloads.GENERATORS[name](3 << 20, seed=71).tobytes()
+    rng = np.random.default_rng(3)
+
+    def blocks_of(data):
+        pos = 0
+        while pos < len(data):
+            n = int(rng.integers(1, 700000))
+            yield data[pos:pos + n]
+            pos += n
+
+    for data in (d, d[:1500000] + b"\x01" + d[1500001:], d[:5] + b"\x01" + d[6:], d[:len(d) - 7], d[:100]):
+        out = bytearray()
+        st, cnt = prog.run_stream(blocks_of(data), out.extend)
+        est, eout, ecnt = oracle_run(ssts, data)
+        assert st == est and bytes(out) == eout and (st == 0 or cnt == ecnt), (name, len(data))
+    out = bytearray()
+    assert prog.run_stream(iter(()), out.extend)[0] == oracle_run(ssts, b"")[0]
+
+
+def test_block_streaming_unsupported_program():
+    from kleenexlang_b200.runtime import KexError
+    src = 'start: p >> a\np := /[ab]/*\na := /a/ "x" | /b/\n'
+    prog, _ = gpu_prog(src)
+    with pytest.raises(KexError) as ei:
+        prog.run_stream(iter([b"ab"]), lambda b: None)
+    assert ei.value.code == -4

@@ -93,3 +93,20 @@ def test_compiled_binary_contract(tmp_path):
     cut = d.index(b"\n", 100) + 2                            # inside the numeric id of a later row
     bad = subprocess.run([out], input=d[:cut] + b"x" + d[cut + 1:], capture_output=True)
     assert bad.returncode == 1 and bad.stderr == b"Match error at input symbol %d!\n" % cut
+
+
+@pytest.mark.gpu
+def test_launcher_streams_large_inputs(tmp_path):
+    """Inputs larger than one block go through kex_stream_* (bounded memory);
+    with 1 MiB blocks a 6 MiB input streams and must equal the whole-input run."""
+    from kleenexlang_b200 import workloads
+    out = _compile(tmp_path, "csv2json", "--quiet")
+    d = workloads.gen_csv(6 << 20, seed=8).tobytes()
+    whole = subprocess.run([out], input=d, capture_output=True, env=dict(os.environ, KEX_NO_STREAM="1"))
+    streamed = subprocess.run([out], input=d, capture_output=True, env=dict(os.environ, KEX_STREAM_BLOCK_MIB="1"))
+    assert whole.returncode == streamed.returncode == 0 and whole.stdout == streamed.stdout
+    cut = d.index(b"\n", 3 << 20) + 2
+    bad = d[:cut] + b"x" + d[cut + 1:]
+    w = subprocess.run([out], input=bad, capture_output=True, env=dict(os.environ, KEX_NO_STREAM="1"))
+    s2 = subprocess.run([out], input=bad, capture_output=True, env=dict(os.environ, KEX_STREAM_BLOCK_MIB="1"))
+    assert w.returncode == s2.returncode == 1 and w.stdout == s2.stdout and w.stderr == s2.stderr
