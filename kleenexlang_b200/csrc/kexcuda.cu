@@ -1944,7 +1944,7 @@ extern "C" int kex_stream_end(kex_program *p, uint8_t *h_out, size_t out_cap, si
 static int run_host_pipelined(kex_program *p, const uint8_t *h_in, size_t n, uint8_t *h_out, size_t out_cap,
                               size_t *out_len, int *status, size_t *fail_count, size_t wave) {
   PhaseHost &ph = p->phases[0];
-  const uint32_t Q1 = ph.dev.Q + 1, NL = ph.fdev.NL;
+  const uint32_t NL = ph.fdev.NL;
   if (!p->s_comp) {
     CK(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
@@ -1981,8 +1981,7 @@ static int run_host_pipelined(kex_program *p, const uint8_t *h_in, size_t n, uin
     CK(cudaEventRecord(p->pipe_ev[2 * i], p->s_h2d));
   }
   cudaStream_t st = p->s_comp;
-  std::vector<uint16_t> map(Q1);
-  std::vector<uint8_t> seam(NL), seam_prev(NL);
+  std::vector<uint8_t> seam(NL);
   uint32_t state = ph.dev.init;
   size_t out_off = 0, n_fail = (size_t)-1;
   long pending = -1;                    // sub-wave walked but not yet emitted
@@ -2014,7 +2013,6 @@ static int run_host_pipelined(kex_program *p, const uint8_t *h_in, size_t n, uin
     CK(cudaStreamWaitEvent(st, p->pipe_ev[2 * i], 0));
     p->launches = 0;
     if ((rc = do_summarize(p, 0, d_in + off, len, st))) break;
-    if ((rc = fetch_sync(p, map.data(), p->c->maps[p->c->nlevels - 1].p, Q1 * sizeof(uint16_t), st))) break;
     uint32_t end_state = 0;
     size_t fpos = (size_t)-1;
     if ((rc = shard_walk_seam(p, state, &end_state, &fpos, seam.data(), st))) break;
@@ -2027,14 +2025,12 @@ static int run_host_pipelined(kex_program *p, const uint8_t *h_in, size_t n, uin
       bool constant = true;
       for (uint32_t l = 1; l < NL; ++l) constant = constant && seam[l] == seam[0];
       if (!constant && !failed) { gave_up = true; break; }
-      const uint32_t code = failed ? seam[0] : seam[0];
-      if ((rc = emit_one((size_t)pending, code, pending_neff))) break;
+      if ((rc = emit_one((size_t)pending, seam[0], pending_neff))) break;    // (after a failure: the code of "nothing live")
       pending = -1;
     }
     pending = (long)i;
     pending_neff = n_eff;
     state = end_state;
-    (void)map;
   }
   if (rc == KEX_OK && !gave_up && pending >= 0) {
     // the last sub-wave: the end-of-input action (or the failure) fixes its seam code
