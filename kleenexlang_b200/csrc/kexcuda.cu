@@ -631,6 +631,7 @@ __global__ void k_publish(const uint8_t *__restrict__ src, volatile uint8_t *dst
 
 #include "kex_fast.cuh"
 #include "kex_v3.cuh"
+#include "kex_act.cuh"
 
 // =================================================================== host
 struct PhaseHost {
@@ -659,12 +660,20 @@ struct PhaseHost {
   size_t smem_fwd3 = 0, smem_seams3 = 0;
   uint32_t v3_stage = 3072;           // per-warp staging window; follows the observed out/in ratio
   uint32_t v3_reccap = V3_RECCAP;     // template records per tile kept in shared memory; follows the observed maximum
+  // action-interpreter phase (kex_act.cuh): no SST tables at all
+  bool act = false;
+  uint32_t act_nregs = 0;
   size_t tile() const { return v3.ok ? (size_t)V3_TILE : (size_t)KEX_CHUNK; }
 };
 
 struct Buf {
   void *p = nullptr;
   size_t cap = 0;
+};
+
+// scratch of the action-interpreter kernels
+struct ActScratch {
+  Buf delta, mn, mx, h0, fate, add, gfate, gadd, gvec, vec, wlen, ctl;
 };
 
 // Scratch of one run / shard in flight (grow-only device buffers and the state
@@ -697,6 +706,7 @@ struct kex_program {
   Ctx cx[2];
   Ctx *c = &cx[0];
   Buf inter[2], hostio_in, hostio_out;
+  ActScratch as;
   // block streaming (kex_stream_*): two blocks resident, the older one waits for its seam code
   Buf sin[2], sout;
   bool st_open = false, st_failed = false;
@@ -959,6 +969,17 @@ static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph
 }
 
 static int load_phase(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
+  if (len >= 32 && rd32(b, 0) == 0x4158454Bu) {          // "KEXA": action-interpreter phase
+    if (rd32(b, 4) != 1u || rd32(b, 12) != ACT_ESC || rd32(b, 16) != len) return KEX_ERR_BAD_BLOB;
+    const uint32_t nregs = rd32(b, 8);
+    if (nregs + 1u > ACT_NSLOT) return KEX_ERR_UNSUPPORTED;
+    memset(&ph.dev, 0, sizeof(ph.dev));
+    ph.dev.R = nregs;
+    ph.dev.max_out = 1;                                    // the interpreter never adds bytes
+    ph.act = true;
+    ph.act_nregs = nregs;
+    return KEX_OK;
+  }
   if (len < 96 || rd32(b, 0) != 0x5058454Bu || rd32(b, 4) != 1u) return KEX_ERR_BAD_BLOB;
   const uint32_t Q = rd32(b, 8), C = rd32(b, 12), R = rd32(b, 16), A = rd32(b, 20);
   const uint32_t npieces = rd32(b, 24), nconst = rd32(b, 28), init = rd32(b, 32), maxout = rd32(b, 36);
@@ -1113,6 +1134,11 @@ extern "C" void kex_free(kex_program *p) {
     if (c.hpub) cudaFreeHost(c.hpub);
   }
   for (Buf *b : {&p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out, &p->sin[0], &p->sin[1], &p->sout}) cudaFree(b->p);
+  {
+    ActScratch &a = p->as;
+    Buf *abs[] = {&a.delta, &a.mn, &a.mx, &a.h0, &a.fate, &a.add, &a.gfate, &a.gadd, &a.gvec, &a.vec, &a.wlen, &a.ctl};
+    for (Buf *b : abs) cudaFree(b->p);
+  }
   if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
   if (p->s_comp) cudaStreamDestroy(p->s_comp);
   if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
@@ -1128,6 +1154,7 @@ extern "C" int kex_info(const kex_program *p, uint32_t phase, kex_info_t *info) 
   info->nstates = d.Q; info->nclasses = d.C; info->nregs = d.R; info->nactions = d.A;
   info->max_out_per_byte = d.max_out; info->chunk_bytes = (uint32_t)p->phases[phase].tile();
   info->monoid_kernels = p->phases[phase].fast ? 1u : 0u;
+  if (p->phases[phase].act) info->chunk_bytes = 1024u;
   return KEX_OK;
 }
 
@@ -1141,6 +1168,7 @@ extern "C" int kex_final_action(const kex_program *p, uint32_t state, int *accep
                                 const uint8_t **tail, size_t *tail_len) {
   if (!p) return KEX_ERR_ARG;
   const PhaseHost &ph = p->phases[p->c->sh_phase];
+  if (ph.act) return KEX_ERR_UNSUPPORTED;
   if (state > ph.dev.Q) return KEX_ERR_ARG;
   const int32_t a = ph.fin[state];
   if (accepting) *accepting = a >= 0;
@@ -1706,9 +1734,73 @@ extern "C" int kex_shard_emit(kex_program *p, uint32_t live_end_mask, size_t n_e
 }
 
 // ------------------------------------------------------------ whole pipeline
+// Action-interpreter phase over an action stream resident on the device
+// (kex_act.cuh).  The stream of a stage that rejected in its transducer phase is
+// interpreted as far as it goes (the bottom builder is the result).
+static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, uint8_t *d_out,
+                         size_t out_cap, size_t *out_len, cudaStream_t st) {
+  const PhaseHost &ph = p->phases[phase];
+  *out_len = 0;
+  if (n == 0) return KEX_OK;
+  if (n >= 0xFFFFFFF0ull) return KEX_ERR_UNSUPPORTED;      // 32-bit positions
+  uint32_t tile = 1024;
+  if (const char *e = getenv("KEX_ACT_TILE")) { const long x = atol(e); if (x > 0) tile = (uint32_t)x; }
+  const size_t ntiles = (n + tile - 1) / tile, ngroups = (ntiles + ACT_GROUP - 1) / ACT_GROUP;
+  ActScratch &a = p->as;
+  int rc;
+  if ((rc = ensure(p, a.delta, 4 * ntiles)) || (rc = ensure(p, a.mn, 4 * ntiles)) || (rc = ensure(p, a.mx, 4 * ntiles)) ||
+      (rc = ensure(p, a.h0, 4 * (ntiles + 1))) || (rc = ensure(p, a.fate, (size_t)ACT_NSLOT * ntiles)) ||
+      (rc = ensure(p, a.add, 4ull * ACT_NSLOT * ntiles)) || (rc = ensure(p, a.gfate, (size_t)ACT_NSLOT * ngroups)) ||
+      (rc = ensure(p, a.gadd, 4ull * ACT_NSLOT * ngroups)) || (rc = ensure(p, a.gvec, 4ull * ACT_NSLOT * (ngroups + 1))) ||
+      (rc = ensure(p, a.vec, 4ull * ACT_NSLOT * ntiles)) || (rc = ensure(p, a.wlen, 4ull * (n / 2 + 1))) ||
+      (rc = ensure(p, a.ctl, sizeof(ActCtl))))
+    return rc;
+  ActCtl *ctl = (ActCtl *)a.ctl.p;
+  int32_t *delta = (int32_t *)a.delta.p, *mn = (int32_t *)a.mn.p, *mx = (int32_t *)a.mx.p, *h0 = (int32_t *)a.h0.p;
+  uint8_t *fate = (uint8_t *)a.fate.p, *gfate = (uint8_t *)a.gfate.p;
+  uint32_t *add = (uint32_t *)a.add.p, *gadd = (uint32_t *)a.gadd.p, *gvec = (uint32_t *)a.gvec.p,
+           *vec = (uint32_t *)a.vec.p, *wlen = (uint32_t *)a.wlen.p;
+  const unsigned tb = (unsigned)((ntiles + 127) / 128), gb = (unsigned)((ngroups + 127) / 128);
+  ActCtl h;
+  CK(cudaMemsetAsync(ctl, 0, sizeof(ActCtl), st));
+  ka_heights<<<tb, 128, 0, st>>>(d_in, n, tile, ntiles, ph.act_nregs, delta, mn, mx, ctl);
+  ka_height_scan<<<1, 1024, 0, st>>>(delta, mn, mx, ntiles, ph.act_nregs, h0, ctl);
+  p->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (h.err & 5u) return KEX_ERR_ARG;                      // not an action stream
+  if (h.err & 2u) return KEX_ERR_UNSUPPORTED;              // builders nested deeper than the slots allow
+  ka_fwd_summary<<<tb, 128, 0, st>>>(d_in, n, tile, ntiles, h0, fate, add);
+  ka_group_compose<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gfate, gadd);
+  ka_group_scan<<<1, 32, 0, st>>>(gfate, gadd, ngroups, gvec);
+  ka_tile_vectors<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gvec, vec);
+  ka_fwd_exact<<<tb, 128, 0, st>>>(d_in, n, tile, ntiles, h0, vec, wlen, fate, add, ctl);
+  p->launches += 5;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *out_len = h.total;
+  if (h.total > out_cap) return KEX_ERR_OUT_CAP;
+  if (h.total == 0) return KEX_OK;
+  ka_group_bcompose<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gfate, gadd);
+  ka_group_bscan<<<1, 32, 0, st>>>(gfate, gadd, ngroups, ctl, gvec);
+  ka_tile_bvectors<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gvec, vec);
+  ka_write<<<tb, 128, 0, st>>>(d_in, n, tile, ntiles, h0, vec, wlen, d_out);
+  p->launches += 4;
+  CK(cudaGetLastError());
+  return KEX_OK;
+}
+
 static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
                      size_t *out_len, int *status, size_t *fail_count, cudaStream_t st) {
   PhaseHost &ph = p->phases[phase];
+  if (ph.act) {
+    // status and count are the transducer phase's (kex_run_device keeps them)
+    *status = KEX_ACCEPT;
+    *fail_count = 0;
+    return run_phase_act(p, phase, d_in, n, d_out, out_cap, out_len, st);
+  }
   const PhaseDev &P = ph.dev;
   p->c->sh_phase = phase;
   uint32_t end_state = P.init;
@@ -1789,6 +1881,14 @@ extern "C" int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n, uin
       rc = run_phase(p, (uint32_t)i, cur, cur_n, dst, cap, &ol, &stt, &fc, st);
     }
     if (rc) { *out_len = ol; return rc; }
+    if (p->phases[i].act && i > first && *status == KEX_REJECT) {
+      // the two phases of a stage with register actions are one stage of the
+      // program: a reject of its transducer phase is the stage's reject, and
+      // only whole 16 KiB flushes of the interpreted stream leave it
+      stt = KEX_REJECT;
+      fc = *fail_count;
+      ol = ol / 16384 * 16384;
+    }
     // a rejecting phase hands its truncated stream to the next phase, and the
     // pipeline's exit status is the last phase's (crt.c:414-455)
     *status = stt;

@@ -8,6 +8,7 @@ determinization, optional constant-propagation optimisation.
 from .kleenex import parse_kleenex, desugar
 from .fst import construct_transducer, run_lockstep, run_actions
 from .sst import sst_from_fst, optimize, run_sst
+from .actions import ActStage, action_stream_fst, run_act_stream
 
 
 def build_transducers(src: str):
@@ -16,10 +17,20 @@ def build_transducers(src: str):
     return [construct_transducer(rdecls, ident) for ident in pl]
 
 
-def build_ssts(src: str, opt: int = 3):
+def build_ssts(src: str, opt: int = 3, actions: bool = False):
     """-> [SST] (one per pipeline stage), as `kexc compile --act=false
-    --la=false --opt <opt>` would determinize them."""
-    return [optimize(sst_from_fst(t), opt) for t in build_transducers(src)]
+    --la=false --opt <opt>` would determinize them.  Like the reference
+    (Commands.hs:166-168) this refuses transducers with register actions unless
+    `actions` is set: such a stage then becomes two phases, an SST that writes
+    the action stream and an `ActStage` that interprets it (frontend/actions.py)."""
+    out = []
+    for t in build_transducers(src):
+        if actions and t.has_actions():
+            t2, act = action_stream_fst(t)
+            out += [optimize(sst_from_fst(t2), opt), act]
+        else:
+            out.append(optimize(sst_from_fst(t), opt))
+    return out
 
 
 def simulate_lockstep(src: str, data: bytes):
@@ -36,6 +47,9 @@ def simulate_lockstep(src: str, data: bytes):
 def simulate_sst(ssts, data: bytes):
     """`kexc simulate --sim=sst` over a pipeline; None on reject."""
     for s in ssts:
+        if isinstance(s, ActStage):
+            data = run_act_stream(data)
+            continue
         ok, data, _ = run_sst(s, data)
         if not ok:
             return None

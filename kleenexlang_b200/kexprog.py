@@ -32,6 +32,7 @@ from .frontend import byteset as BS
 
 MAGIC_PHASE = 0x5058454B      # "KEXP"
 MAGIC_PIPE = 0x4C58454B       # "KEXL"
+MAGIC_ACT = 0x4158454B        # "KEXA": action-interpreter phase (frontend/actions.py, csrc/kex_act.cuh)
 VERSION = 1
 DEAD = 0xFF
 MAX_REGS = 32
@@ -308,8 +309,14 @@ def serialize_phase(t: PhaseTables, with_fast: bool = True) -> bytes:
     return struct.pack("<%dI" % nhdr, *hdr) + bytes(body)
 
 
+def serialize_act(stage) -> bytes:
+    """Action-interpreter phase: nothing but the register count and the escape byte."""
+    from .frontend.actions import ESC
+    return struct.pack("<8I", MAGIC_ACT, VERSION, stage.nregs, ESC, 32, 0, 0, 0)
+
+
 def serialize_pipeline(phases, with_fast: bool = True) -> bytes:
-    blobs = [serialize_phase(t, with_fast) for t in phases]
+    blobs = [serialize_act(t) if hasattr(t, "nregs") else serialize_phase(t, with_fast) for t in phases]
     n = len(blobs)
     hdr_words = 4 + 2 * n
     hdr_size = (hdr_words * 4 + 15) // 16 * 16
@@ -323,12 +330,20 @@ def serialize_pipeline(phases, with_fast: bool = True) -> bytes:
     return hdr + b"".join(blobs)
 
 
-def compile_kex(src: str, opt: int = 3, with_fast: bool = True) -> bytes:
+def compile_kex(src: str, opt: int = 3, with_fast: bool = True, actions: bool = True) -> bytes:
     """`.kex` source -> kexprog blob (the CUDA counterpart of
-    `kexc compile --act=false --la=false`)."""
+    `kexc compile --act=false --la=false`).  A stage with register actions
+    (`reg@t`, `!reg`), which the reference only compiles in its oracle/action
+    mode, becomes two phases here as well: a transducer phase that writes the
+    action stream and an action-interpreter phase (frontend/actions.py);
+    `actions=False` refuses such programs like `--act=false` does."""
     from .frontend.driver import build_ssts
     phases = []
-    for s in build_ssts(src, opt):
+    s0s = None
+    for s in build_ssts(src, opt, actions=actions):
+        if hasattr(s, "nregs"):
+            phases.append(s)
+            continue
         try:
             phases.append(build_phase(s))
         except UnsupportedProgram:
@@ -336,6 +351,7 @@ def compile_kex(src: str, opt: int = 3, with_fast: bool = True) -> bytes:
                 raise
             # constant propagation may move a literal in front of an older
             # register; the unoptimised SST always has the required shape
-            s0 = build_ssts(src, 0)[len(phases)]
-            phases.append(build_phase(s0))
+            if s0s is None:
+                s0s = build_ssts(src, 0, actions=actions)
+            phases.append(build_phase(s0s[len(phases)]))
     return serialize_pipeline(phases, with_fast)

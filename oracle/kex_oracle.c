@@ -179,3 +179,69 @@ int kex_oracle_run(const void *sst, size_t sstlen, const uint8_t *in, size_t n, 
   free(o);
   return ovf ? -3 : status;
 }
+
+/*
+ * Action interpreter over an action stream (ORACLE, as above): a stack of
+ * output builders plus a register bank -- the action semantics of
+ * src/KMC/Kleenex/Actions.hs:14-58, i.e. what `interp` makes of the symbols in
+ * src/KMC/SymbolicSST/ActionSST.hs:83-104.  Stream encoding: see
+ * kleenexlang_b200/frontend/actions.py (ESC = 0xFF; ESC 0 literal, ESC 1 push,
+ * ESC 2+2r pop r, ESC 3+2r write r).  The result is the bottom builder.
+ * Returns 0, -3 (output does not fit; *outlen = needed) or -1 (malformed).
+ */
+typedef struct { uint8_t *d; size_t len, cap; } abuf;
+static void abuf_put(abuf *b, const uint8_t *s, size_t n) {
+  if (b->len + n > b->cap) {
+    size_t c = b->cap ? b->cap : 64;
+    while (c < b->len + n) c *= 2;
+    b->d = (uint8_t *)realloc(b->d, c);
+    b->cap = c;
+  }
+  if (n) memcpy(b->d + b->len, s, n);
+  b->len += n;
+}
+int kex_oracle_act(const uint8_t *in, size_t n, uint32_t nregs, uint8_t *out, size_t cap, size_t *outlen) {
+  size_t depth = 0, scap = 8;
+  abuf *stack = (abuf *)calloc(scap, sizeof(abuf));
+  abuf *regs = (abuf *)calloc(nregs ? nregs : 1, sizeof(abuf));
+  int rc = 0;
+  for (size_t i = 0; i < n && rc == 0; ++i) {
+    const uint8_t b = in[i];
+    if (b != 0xFF) { abuf_put(&stack[depth], &b, 1); continue; }
+    if (i + 1 >= n) break;                      /* truncated stream: lone ESC */
+    const uint32_t c = in[++i];
+    if (c == 0) { abuf_put(&stack[depth], &b, 1); }
+    else if (c == 1) {
+      if (++depth == scap) {
+        stack = (abuf *)realloc(stack, 2 * scap * sizeof(abuf));
+        memset(stack + scap, 0, scap * sizeof(abuf));
+        scap *= 2;
+      }
+      stack[depth].len = 0;
+    } else {
+      const uint32_t r = (c & 1) ? (c - 3) / 2 : (c - 2) / 2;
+      if (r >= nregs) { rc = -1; break; }
+      if (c & 1) {                              /* write r: append and clear */
+        abuf_put(&stack[depth], regs[r].d, regs[r].len);
+        regs[r].len = 0;
+      } else {                                  /* pop r: the top builder becomes r */
+        if (depth == 0) { rc = -1; break; }
+        abuf t = regs[r];
+        regs[r] = stack[depth];
+        stack[depth] = t;
+        stack[depth].len = 0;
+        --depth;
+      }
+    }
+  }
+  if (rc == 0) {
+    *outlen = stack[0].len;
+    if (stack[0].len > cap) rc = -3;
+    else if (stack[0].len) memcpy(out, stack[0].d, stack[0].len);
+  }
+  for (size_t k = 0; k < scap; ++k) free(stack[k].d);
+  for (uint32_t r = 0; r < nregs; ++r) free(regs[r].d);
+  free(stack);
+  free(regs);
+  return rc;
+}

@@ -67,8 +67,22 @@ def oracle_run(ssts, data: bytes):
         _lib.kex_oracle_run.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                         ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
                                         ctypes.POINTER(ctypes.c_size_t)]
+        _lib.kex_oracle_act.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p,
+                                        ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     status, count = 0, 0
     for s in ssts:
+        if hasattr(s, "nregs"):
+            # action interpreter phase (frontend/actions.py); a stage that rejected in its
+            # transducer phase stays rejected and keeps whole 16 KiB flushes only
+            buf = ctypes.create_string_buffer(max(1, len(data)))
+            ol = ctypes.c_size_t()
+            rc = _lib.kex_oracle_act(data, len(data), s.nregs, buf, len(data), ctypes.byref(ol))
+            if rc < 0:
+                raise RuntimeError("oracle: malformed action stream")
+            data = buf.raw[:ol.value]
+            if status:
+                data = data[:len(data) // 16384 * 16384]
+            continue
         blob = s if isinstance(s, (bytes, bytearray)) else serialize_sst(s)
         cap = max(4096, 4 * len(data) + 4096)
         while True:

@@ -1,0 +1,131 @@
+"""Register actions (`reg@t`, `!reg`, `[reg <- ..]`): the two-phase stage
+(transducer phase writing an action stream + action interpreter,
+kleenexlang_b200/frontend/actions.py) against the reference's semantics --
+the lockstep FST simulation followed by the action interpretation of
+src/KMC/Kleenex/Actions.hs -- and the CPU model of the device algorithm."""
+import ctypes
+import os
+import random
+import struct
+
+import pytest
+
+from conftest import load_vectors, vec_matches
+from action_cases import NAMES, source, gen, rejecting
+from act_model import run_model
+from kleenexlang_b200.frontend.actions import ESC, run_act_stream, decode_stream
+from kleenexlang_b200.frontend.driver import build_ssts, simulate_lockstep, simulate_sst
+from kleenexlang_b200.kexprog import compile_kex, MAGIC_ACT
+from oracle.sstbin import oracle_run
+
+REG_VECS = [v for v in load_vectors() if v["uses_registers"]]
+
+
+def random_stream(rng, n, nregs, maxd):
+    out = bytearray()
+    d = 0
+    for _ in range(n):
+        x = rng.random()
+        if x < 0.5:
+            b = rng.choice([ESC, 0, 1, 2, 65, 66, 67, 254])
+            out += bytes([ESC, 0]) if b == ESC else bytes([b])
+        elif x < 0.65 and d < maxd:
+            out += bytes([ESC, 1])
+            d += 1
+        elif x < 0.8 and d > 0:
+            out += bytes([ESC, 2 + 2 * rng.randrange(nregs)])
+            d -= 1
+        else:
+            out += bytes([ESC, 3 + 2 * rng.randrange(nregs)])
+    return bytes(out)
+
+
+@pytest.mark.parametrize("opt", [0, 3])
+@pytest.mark.parametrize("v", REG_VECS, ids=[v["name"] for v in REG_VECS])
+def test_reference_vectors_with_registers(v, opt):
+    # the reference's own golden vectors of programs with register actions
+    ssts = build_ssts(v["program"], opt, actions=True)
+    try:
+        assert vec_matches(v, simulate_sst(ssts, v["input"]))
+        st, out, _ = oracle_run(ssts, v["input"])
+    except MemoryError:
+        pytest.skip("SST too large")
+    assert st == 0 and vec_matches(v, out)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_two_phase_stage_equals_lockstep_semantics(name):
+    src = source(name)
+    ssts = build_ssts(src, 3, actions=True)
+    for seed, size in [(0, 0), (1, 30), (2, 300), (3, 2000)]:
+        data = gen(name, size, seed)
+        exp = simulate_lockstep(src, data)
+        assert exp is not None
+        assert simulate_sst(ssts, data) == exp
+        assert oracle_run(ssts, data)[:2] == (0, exp)
+        bad = rejecting(name, data)
+        if bad is not None:
+            assert simulate_lockstep(src, bad) is None
+            assert oracle_run(ssts, bad)[0] == 1
+
+
+def test_action_interpreter_c_oracle_equals_python():
+    rng = random.Random(5)
+    from oracle import sstbin
+    lib = ctypes.CDLL(sstbin.build_lib())
+    lib.kex_oracle_act.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p,
+                                   ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    for _ in range(300):
+        nregs = rng.randrange(1, 5)
+        s = random_stream(rng, rng.randrange(0, 200), nregs, rng.randrange(1, 6))
+        if rng.random() < 0.2 and s:
+            s = s[:rng.randrange(len(s))]
+        buf = ctypes.create_string_buffer(len(s) + 1)
+        ol = ctypes.c_size_t()
+        assert lib.kex_oracle_act(s, len(s), nregs, buf, len(s), ctypes.byref(ol)) == 0
+        assert buf.raw[:ol.value] == run_act_stream(s)
+
+
+def test_device_algorithm_model():
+    # the five passes of csrc/kex_act.cuh, tile by tile, at every seam position
+    rng = random.Random(1)
+    for it in range(600):
+        nregs = rng.randrange(1, 5)
+        s = random_stream(rng, rng.randrange(0, 120), nregs, rng.randrange(1, 6))
+        if rng.random() < 0.2 and s:
+            s = s[:rng.randrange(len(s))]
+        assert run_model(s, nregs, rng.choice([1, 2, 3, 5, 8, 16, 64]), rng.choice([1, 2, 3, 8])) == run_act_stream(s)
+
+
+def test_escape_roundtrip_and_blob():
+    assert decode_stream(bytes([65, ESC, 0, ESC, 1, ESC, 2, ESC, 5, ESC])) == [65, ESC, ("push",), ("pop", 0), ("write", 1)]
+    blob = compile_kex(source("swap_fields"))
+    nph = struct.unpack_from("<I", blob, 8)[0]
+    assert nph == 2
+    off, ln = struct.unpack_from("<2I", blob, 16 + 8)
+    magic, ver, nregs, esc, total = struct.unpack_from("<5I", blob, off)
+    assert (magic, ver, nregs, esc, total, ln) == (MAGIC_ACT, 1, 2, ESC, 32, 32)
+    with pytest.raises(ValueError):
+        compile_kex(source("swap_fields"), actions=False)      # like `--act=false` (Commands.hs:166-168)
+
+
+BENCH = "/root/reference/bench/kleenex/src"
+BENCH_INPUTS = {
+    "swap_lines": b"first line\nsecond\n",
+    "sort_ab": b"abbabaabbb",
+    "worstcase": b"xyzzy",
+    "drex_rev-dict": b"a=1;bb=22;;c;",
+    "mitm": b"<p><form action=\"http://x/y\" ><input></form><form  action='u'>",
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(BENCH), reason="reference checkout not present")
+@pytest.mark.parametrize("name", sorted(BENCH_INPUTS))
+def test_reference_bench_programs_with_actions(name):
+    src = open(os.path.join(BENCH, name + ".kex"), encoding="utf-8").read()
+    data = BENCH_INPUTS[name]
+    exp = simulate_lockstep(src, data)
+    assert exp is not None
+    ssts = build_ssts(src, 3, actions=True)
+    assert oracle_run(ssts, data)[:2] == (0, exp)
+    compile_kex(src)

@@ -1,0 +1,100 @@
+"""Parity of the action-interpreter kernels (csrc/kex_act.cuh) and of whole
+programs with register actions, through the C ABI, with the CPU oracle
+(oracle/kex_oracle.c: kex_oracle_run + kex_oracle_act).  Bit-exact."""
+import os
+import random
+import struct
+
+import pytest
+
+from action_cases import NAMES, source, gen, rejecting
+from test_actions import random_stream
+from kleenexlang_b200.frontend.actions import ESC, run_act_stream
+from kleenexlang_b200.frontend.driver import build_ssts
+from kleenexlang_b200.kexprog import compile_kex, MAGIC_ACT, MAGIC_PIPE, VERSION
+from oracle.sstbin import oracle_run
+
+pytestmark = pytest.mark.gpu
+_cache = {}
+
+
+def gpu_prog(name):
+    from kleenexlang_b200.runtime import CompiledProgram
+    if name not in _cache:
+        src = source(name)
+        _cache[name] = (CompiledProgram(compile_kex(src)), build_ssts(src, 3, actions=True))
+    return _cache[name]
+
+
+@pytest.fixture(params=[16, 48, 1024])
+def act_tile(request):
+    # small tiles put a seam at (nearly) every token boundary
+    os.environ["KEX_ACT_TILE"] = str(request.param)
+    yield request.param
+    del os.environ["KEX_ACT_TILE"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_action_programs(name, act_tile):
+    prog, ssts = gpu_prog(name)
+    for seed, size in [(0, 0), (1, 40), (2, 700), (3, 20000), (4, 300000)]:
+        d = gen(name, size, seed)
+        est, eout, _ = oracle_run(ssts, d)
+        assert est == 0
+        st, out, _ = prog.run(d)
+        assert (st, out) == (est, eout), (name, size)
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES if rejecting(n, b"") is not None])
+def test_action_programs_reject(name):
+    prog, ssts = gpu_prog(name)
+    for seed, size in [(1, 40), (2, 40000)]:
+        bad = rejecting(name, gen(name, size, seed))
+        est, eout, ecnt = oracle_run(ssts, bad)
+        assert est == 1
+        assert prog.run(bad) == (est, eout, ecnt)
+
+
+def test_action_program_large():
+    # 24 MiB: ~24 K tiles, ~100 groups; size-independent check as well (swapping twice is the identity)
+    prog, ssts = gpu_prog("swap_fields")
+    d = gen("swap_fields", 24 << 20, 9)
+    st, out, _ = prog.run(d)
+    est, eout, _ = oracle_run(ssts, d)
+    assert (st, out) == (est, eout)
+    st2, back, _ = prog.run(out)
+    assert st2 == 0 and back == d
+    prog, ssts = gpu_prog("reverse_items")
+    d = gen("reverse_items", 6 << 20, 10)
+    st, out, _ = prog.run(d)
+    assert (st, out) == oracle_run(ssts, d)[:2]
+    assert prog.run(out)[1] == d                      # reversing twice
+
+
+def act_only_blob(nregs):
+    ph = struct.pack("<8I", MAGIC_ACT, VERSION, nregs, ESC, 32, 0, 0, 0)
+    return struct.pack("<8I", MAGIC_PIPE, VERSION, 1, 32 + len(ph), 32, len(ph), 0, 0) + ph
+
+
+def test_interpreter_kernels_on_random_streams(act_tile):
+    from kleenexlang_b200.runtime import CompiledProgram
+    rng = random.Random(act_tile)
+    progs = {k: CompiledProgram(act_only_blob(k)) for k in (1, 2, 4)}
+    for it in range(60):
+        nregs = rng.choice([1, 2, 4])
+        s = random_stream(rng, rng.choice([0, 5, 50, 400, 4000, 30000]), nregs, rng.randrange(1, 8))
+        if rng.random() < 0.3 and s:
+            s = s[:rng.randrange(len(s))]
+        st, out, _ = progs[nregs].run(s)
+        assert st == 0 and out == run_act_stream(s), (it, len(s))
+
+
+def test_interpreter_refuses_what_it_cannot_hold():
+    from kleenexlang_b200.runtime import CompiledProgram, KexError
+    prog = CompiledProgram(act_only_blob(2))
+    with pytest.raises(KexError):
+        prog.run(bytes([ESC, 2]))                      # pop on the bottom builder: not an action stream
+    with pytest.raises(KexError):
+        prog.run(bytes([ESC, 1]) * 40)                 # 40 nested builders > 32 slots
+    with pytest.raises(KexError):
+        prog.run(bytes([ESC, 3 + 2 * 7]))              # register 7 of 2
