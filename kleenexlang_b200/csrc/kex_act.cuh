@@ -27,8 +27,9 @@
 // the tile, which undoes the tokens: `write r` needs the length R[r] had, kept
 // per token by the exact forward walk (wlen[operand position / 2]).
 //
-// One thread per tile in every pass (tests/act_model.py is the same algorithm
-// in Python, checked against the oracle on CPU).
+// One thread per tile in the passes over the stream, one warp (lane = slot) per
+// group of tiles in the scans (tests/act_model.py is the same algorithm in
+// Python, checked against the oracle on CPU).
 #pragma once
 
 #define ACT_ESC 0xFFu
@@ -44,26 +45,54 @@ struct ActCtl {
   uint32_t total;                // bytes of the bottom builder at the end of the stream
 };
 
+#define ACT_NT 128u              // threads per block of the per-tile kernels
+
+// Thread-private slot arrays live in shared memory, [slot][thread]: a thread only
+// ever touches its own column (bank = thread), and unlike local memory the
+// footprint cannot fall out of L1 when many blocks are resident.
+#define ACT_S(arr, slot_) arr[(slot_) * ACT_NT + threadIdx.x]
+
+// Four input bytes; the ragged last word of the stream is read byte by byte so
+// that nothing behind it is touched (tiles start on 16-byte boundaries of a
+// 16-byte aligned stream).
+__device__ __forceinline__ uint32_t act_ld4(const uint8_t *__restrict__ in, size_t c, uint32_t cnt) {
+  if (cnt == 4u) return __ldg((const uint32_t *)(in + c));
+  uint32_t w = 0;
+  for (uint32_t k = 0; k < cnt; ++k) w |= (uint32_t)in[c + k] << (8u * k);
+  return w;
+}
+
 // Forward iteration over the tokens of bytes [lo, hi): BYTE(i, v), PUSH(i), POP(i, r), WRITE(i, r).
+// (word loop rolled, four copies of the body: the kernels are bound by instruction fetch otherwise)
 #define ACT_FWD_TOKENS(in, lo, hi, BYTE, PUSH, POP, WRITE)                                   \
   {                                                                                          \
     bool pe_ = (lo) > 0 && (in)[(lo) - 1] == ACT_ESC;                                        \
-    for (size_t i_ = (lo); i_ < (hi); ++i_) {                                                \
-      const uint32_t b_ = (in)[i_];                                                          \
-      if (pe_) {                                                                             \
-        pe_ = false;                                                                         \
-        if (b_ == 0u) { BYTE(i_, ACT_ESC) }                                                  \
-        else if (b_ == 1u) { PUSH(i_) }                                                      \
-        else if (b_ & 1u) { WRITE(i_, (b_ - 3u) >> 1) }                                      \
-        else { POP(i_, (b_ - 2u) >> 1) }                                                     \
-      } else if (b_ == ACT_ESC) {                                                            \
-        pe_ = true;                                                                          \
-      } else { BYTE(i_, b_) }                                                                \
+    _Pragma("unroll 1")                                                                      \
+    for (size_t c_ = (lo); c_ < (hi); c_ += 4) {                                             \
+      const uint32_t cnt_ = ((hi) - c_ < 4) ? (uint32_t)((hi) - c_) : 4u;                    \
+      const uint32_t w_ = act_ld4(in, c_, cnt_);                                             \
+      _Pragma("unroll")                                                                      \
+      for (uint32_t k_ = 0; k_ < 4u; ++k_) {                                                 \
+        if (k_ < cnt_) {                                                                     \
+          const uint32_t b_ = (w_ >> (8u * k_)) & 0xFFu;                                     \
+          const size_t i_ = c_ + k_;                                                         \
+          (void)i_;                                                                          \
+          if (pe_) {                                                                         \
+            pe_ = false;                                                                     \
+            if (b_ == 0u) { BYTE(i_, ACT_ESC) }                                              \
+            else if (b_ == 1u) { PUSH(i_) }                                                  \
+            else if (b_ & 1u) { WRITE(i_, (b_ - 3u) >> 1) }                                  \
+            else { POP(i_, (b_ - 2u) >> 1) }                                                 \
+          } else if (b_ == ACT_ESC) {                                                        \
+            pe_ = true;                                                                      \
+          } else { BYTE(i_, b_) }                                                            \
+        }                                                                                    \
+      }                                                                                      \
     }                                                                                        \
   }
 
 // ---- P0: stack height
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ACT_NT)
 ka_heights(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles, uint32_t nregs,
            int32_t *__restrict__ delta, int32_t *__restrict__ mn, int32_t *__restrict__ mx, ActCtl *ctl) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,75 +145,137 @@ ka_height_scan(const int32_t *__restrict__ delta, const int32_t *__restrict__ mn
   atomicMax(&ctl->hmax, (int32_t)top);
 }
 
-// ---- slot-map primitives (arrays are thread-local)
-__device__ __forceinline__ void act_pop(uint8_t *fate, uint32_t h, uint32_t N) {
-#pragma unroll 4
-  for (int x = 0; x < ACT_NSLOT; ++x) {
-    const uint32_t f = fate[x];
-    fate[x] = (uint8_t)(f == N ? ACT_DEAD : (f == h ? N : f));
+// ---- slot-content bookkeeping of a tile
+// Which slot the OLD content of every slot (its content at the tile start) is in,
+// and where it ends inside that slot, is kept as a forest over the 32 old
+// contents: merging R[r] into the builder links the root of R[r]'s tree under the
+// root of the builder's tree (O(1) per token; the loops over all slots happen
+// once, at the end of the tile).
+//   root[d]    tree whose contents are in current slot d (ACT_DEAD: none)
+//   parent[x]  ACT_DEAD for a root
+//   delta[x]   end offset of x's content inside its slot = len0[x] + sum of delta along the path to the root
+// fate[x] = slot the old content x ended up in (ACT_DEAD: dropped); `sor` is scratch.
+#define ACT_FATES(root, parent, sor, fate)                                                    \
+  {                                                                                           \
+    for (int x_ = 0; x_ < ACT_NSLOT; ++x_) ACT_S(sor, x_) = (uint8_t)ACT_DEAD;                \
+    for (int d_ = 0; d_ < ACT_NSLOT; ++d_) { const uint32_t r_ = ACT_S(root, d_); if (r_ != ACT_DEAD) ACT_S(sor, r_) = (uint8_t)d_; } \
+    for (int x_ = 0; x_ < ACT_NSLOT; ++x_) {                                                  \
+      uint32_t r_ = (uint32_t)x_;                                                             \
+      for (;;) { const uint32_t p_ = ACT_S(parent, r_); if (p_ == ACT_DEAD) break; r_ = p_; } \
+      ACT_S(fate, x_) = ACT_S(sor, r_);                                                       \
+    }                                                                                         \
   }
-}
+
+// A thread's row of a per-tile table is contiguous (32 B of fates, 128 B of
+// lengths): whole-sector vector accesses.
+#define ACT_ST_ROW8(dst, arr)                                                                 \
+  {                                                                                           \
+    uint32_t w_[8];                                                                           \
+    _Pragma("unroll")                                                                         \
+    for (int k_ = 0; k_ < 8; ++k_)                                                            \
+      w_[k_] = (uint32_t)ACT_S(arr, 4 * k_) | ((uint32_t)ACT_S(arr, 4 * k_ + 1) << 8) |       \
+               ((uint32_t)ACT_S(arr, 4 * k_ + 2) << 16) | ((uint32_t)ACT_S(arr, 4 * k_ + 3) << 24); \
+    ((uint4 *)(dst))[0] = make_uint4(w_[0], w_[1], w_[2], w_[3]);                             \
+    ((uint4 *)(dst))[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                             \
+  }
+#define ACT_ST_ROW32(dst, arr)                                                                \
+  {                                                                                           \
+    _Pragma("unroll")                                                                         \
+    for (int k_ = 0; k_ < 8; ++k_)                                                            \
+      ((uint4 *)(dst))[k_] = make_uint4(ACT_S(arr, 4 * k_), ACT_S(arr, 4 * k_ + 1), ACT_S(arr, 4 * k_ + 2), ACT_S(arr, 4 * k_ + 3)); \
+  }
+#define ACT_LD_ROW32(src, arr)                                                                \
+  {                                                                                           \
+    _Pragma("unroll")                                                                         \
+    for (int k_ = 0; k_ < 8; ++k_) {                                                          \
+      const uint4 q_ = ((const uint4 *)(src))[k_];                                            \
+      ACT_S(arr, 4 * k_) = q_.x; ACT_S(arr, 4 * k_ + 1) = q_.y; ACT_S(arr, 4 * k_ + 2) = q_.z; ACT_S(arr, 4 * k_ + 3) = q_.w; \
+    }                                                                                         \
+  }
 
 // ---- P1: forward summary of a tile (fate of every slot's old content, bytes added per slot)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ACT_NT)
 ka_fwd_summary(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles,
                const int32_t *__restrict__ h0, uint8_t *__restrict__ fate_out, uint32_t *__restrict__ add_out) {
+  __shared__ uint32_t add[ACT_NSLOT * ACT_NT];
+  __shared__ uint8_t root[ACT_NSLOT * ACT_NT], parent[ACT_NSLOT * ACT_NT], sor[ACT_NSLOT * ACT_NT], fate[ACT_NSLOT * ACT_NT];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
-  uint8_t fate[ACT_NSLOT];
-  uint32_t add[ACT_NSLOT];
-  for (int x = 0; x < ACT_NSLOT; ++x) { fate[x] = (uint8_t)x; add[x] = 0; }
+  for (int x = 0; x < ACT_NSLOT; ++x) { ACT_S(add, x) = 0; ACT_S(root, x) = (uint8_t)x; ACT_S(parent, x) = (uint8_t)ACT_DEAD; }
   uint32_t h = (uint32_t)h0[t];
-#define A_BYTE(i, v) { add[h] += 1u; }
-#define A_PUSH(i) { ++h; }
-#define A_POP(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r); act_pop(fate, h, N); add[N] = add[h]; add[h] = 0; --h; }
+  uint32_t cur = 0;                                 // add[h], kept in a register while h does not change
+#define A_BYTE(i, v) { cur += 1u; }
+#define A_PUSH(i) { ACT_S(add, h) = cur; ++h; cur = ACT_S(add, h); }
+#define A_POP(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r);                                \
+    ACT_S(root, N) = ACT_S(root, h); ACT_S(root, h) = (uint8_t)ACT_DEAD;                      \
+    ACT_S(add, N) = cur; ACT_S(add, h) = 0; --h; cur = ACT_S(add, h); }
 #define A_WRITE(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r);                              \
-    for (int x = 0; x < ACT_NSLOT; ++x) if (fate[x] == N) fate[x] = (uint8_t)h;               \
-    add[h] += add[N]; add[N] = 0; }
+    const uint32_t rN = ACT_S(root, N);                                                       \
+    if (rN != ACT_DEAD) {                                                                     \
+      const uint32_t rh = ACT_S(root, h);                                                     \
+      if (rh == ACT_DEAD) ACT_S(root, h) = (uint8_t)rN; else ACT_S(parent, rN) = (uint8_t)rh; \
+      ACT_S(root, N) = (uint8_t)ACT_DEAD;                                                     \
+    }                                                                                         \
+    cur += ACT_S(add, N); ACT_S(add, N) = 0; }
   ACT_FWD_TOKENS(in, lo, hi, A_BYTE, A_PUSH, A_POP, A_WRITE)
 #undef A_BYTE
 #undef A_PUSH
 #undef A_POP
 #undef A_WRITE
-  for (int x = 0; x < ACT_NSLOT; ++x) { fate_out[t * ACT_NSLOT + x] = fate[x]; add_out[t * ACT_NSLOT + x] = add[x]; }
+  ACT_S(add, h) = cur;
+  ACT_FATES(root, parent, sor, fate)
+  ACT_ST_ROW8(fate_out + t * ACT_NSLOT, fate)
+  ACT_ST_ROW32(add_out + t * ACT_NSLOT, add)
 }
+
+// The kernels below run one WARP per group of tiles, lane = slot.
 
 // forward composition of the summaries of one group of tiles (earlier first)
 __global__ void __launch_bounds__(128)
 ka_group_compose(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ add, size_t ntiles, size_t ngroups,
                  uint8_t *__restrict__ gfate, uint32_t *__restrict__ gadd) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
   if (g >= ngroups) return;
   const size_t lo = g * ACT_GROUP, hi = (lo + ACT_GROUP < ntiles) ? lo + ACT_GROUP : ntiles;
-  uint8_t f[ACT_NSLOT];
-  uint32_t a[ACT_NSLOT], b[ACT_NSLOT];
-  for (int x = 0; x < ACT_NSLOT; ++x) { f[x] = fate[lo * ACT_NSLOT + x]; a[x] = add[lo * ACT_NSLOT + x]; }
+  uint32_t f = fate[lo * ACT_NSLOT + lane], a = add[lo * ACT_NSLOT + lane];
   for (size_t t = lo + 1; t < hi; ++t) {
-    const uint8_t *f2 = fate + t * ACT_NSLOT;
-    const uint32_t *a2 = add + t * ACT_NSLOT;
-    for (int x = 0; x < ACT_NSLOT; ++x) b[x] = a2[x];
-    for (int m = 0; m < ACT_NSLOT; ++m) { const uint32_t d = f2[m]; if (d != ACT_DEAD) b[d] += a[m]; }
-    for (int x = 0; x < ACT_NSLOT; ++x) { a[x] = b[x]; const uint32_t d = f[x]; f[x] = (uint8_t)(d == ACT_DEAD ? ACT_DEAD : f2[d]); }
+    const uint32_t f2 = fate[t * ACT_NSLOT + lane];
+    uint32_t acc = add[t * ACT_NSLOT + lane];
+#pragma unroll
+    for (int m = 0; m < ACT_NSLOT; ++m) {
+      const uint32_t fm = __shfl_sync(0xFFFFFFFFu, f2, m), am = __shfl_sync(0xFFFFFFFFu, a, m);
+      if (fm == lane) acc += am;
+    }
+    const uint32_t nf = __shfl_sync(0xFFFFFFFFu, f2, f & 31u);
+    f = (f == ACT_DEAD) ? ACT_DEAD : nf;
+    a = acc;
   }
-  for (int x = 0; x < ACT_NSLOT; ++x) { gfate[g * ACT_NSLOT + x] = f[x]; gadd[g * ACT_NSLOT + x] = a[x]; }
+  gfate[g * ACT_NSLOT + lane] = (uint8_t)f;
+  gadd[g * ACT_NSLOT + lane] = a;
 }
 
-// one warp (lane = slot): slot lengths at the start of every group; gvec[ngroups] = at the end of the stream
+// one warp: slot lengths at the start of every group; gvec[ngroups] = at the end of the stream
 __global__ void __launch_bounds__(32)
 ka_group_scan(const uint8_t *__restrict__ gfate, const uint32_t *__restrict__ gadd, size_t ngroups,
               uint32_t *__restrict__ gvec) {
   const uint32_t lane = threadIdx.x;
   uint32_t v = 0;
+  uint32_t f = ngroups ? gfate[lane] : 0u, acc = ngroups ? gadd[lane] : 0u;
   for (size_t g = 0; g < ngroups; ++g) {
     gvec[g * ACT_NSLOT + lane] = v;
-    const uint32_t f = gfate[g * ACT_NSLOT + lane];
-    uint32_t acc = gadd[g * ACT_NSLOT + lane];
+    // the next group's summary is loaded before this one's dependent arithmetic
+    const uint32_t nf = (g + 1 < ngroups) ? gfate[(g + 1) * ACT_NSLOT + lane] : 0u;
+    const uint32_t na = (g + 1 < ngroups) ? gadd[(g + 1) * ACT_NSLOT + lane] : 0u;
+#pragma unroll
     for (int m = 0; m < ACT_NSLOT; ++m) {
       const uint32_t fm = __shfl_sync(0xFFFFFFFFu, f, m), vm = __shfl_sync(0xFFFFFFFFu, v, m);
       if (fm == lane) acc += vm;
     }
     v = acc;
+    f = nf;
+    acc = na;
   }
   gvec[ngroups * ACT_NSLOT + lane] = v;
 }
@@ -193,73 +284,104 @@ ka_group_scan(const uint8_t *__restrict__ gfate, const uint32_t *__restrict__ ga
 __global__ void __launch_bounds__(128)
 ka_tile_vectors(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ add, size_t ntiles, size_t ngroups,
                 const uint32_t *__restrict__ gvec, uint32_t *__restrict__ vec) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
   if (g >= ngroups) return;
   const size_t lo = g * ACT_GROUP, hi = (lo + ACT_GROUP < ntiles) ? lo + ACT_GROUP : ntiles;
-  uint32_t v[ACT_NSLOT], b[ACT_NSLOT];
-  for (int x = 0; x < ACT_NSLOT; ++x) v[x] = gvec[g * ACT_NSLOT + x];
+  uint32_t v = gvec[g * ACT_NSLOT + lane];
   for (size_t t = lo; t < hi; ++t) {
-    for (int x = 0; x < ACT_NSLOT; ++x) { vec[t * ACT_NSLOT + x] = v[x]; b[x] = add[t * ACT_NSLOT + x]; }
-    for (int m = 0; m < ACT_NSLOT; ++m) { const uint32_t d = fate[t * ACT_NSLOT + m]; if (d != ACT_DEAD) b[d] += v[m]; }
-    for (int x = 0; x < ACT_NSLOT; ++x) v[x] = b[x];
+    vec[t * ACT_NSLOT + lane] = v;
+    const uint32_t f = fate[t * ACT_NSLOT + lane];
+    uint32_t acc = add[t * ACT_NSLOT + lane];
+#pragma unroll
+    for (int m = 0; m < ACT_NSLOT; ++m) {
+      const uint32_t fm = __shfl_sync(0xFFFFFFFFu, f, m), vm = __shfl_sync(0xFFFFFFFFu, v, m);
+      if (fm == lane) acc += vm;
+    }
+    v = acc;
   }
 }
 
 // ---- P2: exact lengths; length of R[r] at every `write r`; backward summary of the tile
 // (fate as in P1; tail = bytes behind a slot's old content inside the slot it ended up in)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ACT_NT)
 ka_fwd_exact(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles, const int32_t *__restrict__ h0,
              const uint32_t *__restrict__ vec, uint32_t *__restrict__ wlen, uint8_t *__restrict__ fate_out,
              uint32_t *__restrict__ tail_out, ActCtl *ctl) {
+  __shared__ uint32_t len[ACT_NSLOT * ACT_NT], delta[ACT_NSLOT * ACT_NT];
+  __shared__ uint8_t root[ACT_NSLOT * ACT_NT], parent[ACT_NSLOT * ACT_NT], sor[ACT_NSLOT * ACT_NT], fate[ACT_NSLOT * ACT_NT];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
-  uint8_t fate[ACT_NSLOT];
-  uint32_t len[ACT_NSLOT], endoff[ACT_NSLOT];
-  for (int x = 0; x < ACT_NSLOT; ++x) { fate[x] = (uint8_t)x; len[x] = endoff[x] = vec[t * ACT_NSLOT + x]; }
+  ACT_LD_ROW32(vec + t * ACT_NSLOT, len)
+  for (int x = 0; x < ACT_NSLOT; ++x) { ACT_S(delta, x) = 0; ACT_S(root, x) = (uint8_t)x; ACT_S(parent, x) = (uint8_t)ACT_DEAD; }
   uint32_t h = (uint32_t)h0[t];
-#define A_BYTE(i, v) { len[h] += 1u; }
-#define A_PUSH(i) { ++h; }
-#define A_POP(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r); act_pop(fate, h, N); len[N] = len[h]; len[h] = 0; --h; }
+  uint32_t cur = ACT_S(len, h);                     // len[h], kept in a register while h does not change
+#define A_BYTE(i, v) { cur += 1u; }
+#define A_PUSH(i) { ACT_S(len, h) = cur; ++h; cur = ACT_S(len, h); }
+#define A_POP(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r);                                \
+    ACT_S(root, N) = ACT_S(root, h); ACT_S(root, h) = (uint8_t)ACT_DEAD;                      \
+    ACT_S(len, N) = cur; ACT_S(len, h) = 0; --h; cur = ACT_S(len, h); }
 #define A_WRITE(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r);                              \
-    wlen[(i) >> 1] = len[N];                                                                  \
-    for (int x = 0; x < ACT_NSLOT; ++x) if (fate[x] == N) { fate[x] = (uint8_t)h; endoff[x] += len[h]; } \
-    len[h] += len[N]; len[N] = 0; }
+    const uint32_t ln_ = ACT_S(len, N);                                                       \
+    wlen[(i) >> 1] = ln_;                                                                     \
+    const uint32_t rN = ACT_S(root, N);                                                       \
+    if (rN != ACT_DEAD) {                                                                     \
+      /* R[r]'s contents now end `cur` bytes further into the builder */                     \
+      const uint32_t rh = ACT_S(root, h);                                                     \
+      if (rh == ACT_DEAD) { ACT_S(root, h) = (uint8_t)rN; ACT_S(delta, rN) += cur; }          \
+      else { ACT_S(parent, rN) = (uint8_t)rh; ACT_S(delta, rN) += cur - ACT_S(delta, rh); }   \
+      ACT_S(root, N) = (uint8_t)ACT_DEAD;                                                     \
+    }                                                                                         \
+    cur += ln_; ACT_S(len, N) = 0; }
   ACT_FWD_TOKENS(in, lo, hi, A_BYTE, A_PUSH, A_POP, A_WRITE)
 #undef A_BYTE
 #undef A_PUSH
 #undef A_POP
 #undef A_WRITE
+  ACT_S(len, h) = cur;
+  ACT_FATES(root, parent, sor, fate)
+  // tail[x] = len[fate[x]] - (len0[x] + path sum of delta); it replaces delta[x] only after
+  // every path has been summed (paths run through other slots' deltas)
+  uint32_t tl[ACT_NSLOT];
+  const uint32_t *len0 = vec + t * ACT_NSLOT;
+#pragma unroll 1
   for (int x = 0; x < ACT_NSLOT; ++x) {
-    const uint32_t d = fate[x];
-    fate_out[t * ACT_NSLOT + x] = (uint8_t)d;
-    tail_out[t * ACT_NSLOT + x] = (d == ACT_DEAD) ? 0u : len[d] - endoff[x];
+    const uint32_t d = ACT_S(fate, x);
+    uint32_t endoff = len0[x], r = (uint32_t)x;
+    for (;;) {
+      endoff += ACT_S(delta, r);
+      const uint32_t pr = ACT_S(parent, r);
+      if (pr == ACT_DEAD) break;
+      r = pr;
+    }
+    tl[x] = (d == ACT_DEAD) ? 0u : ACT_S(len, d) - endoff;
   }
-  if (t == ntiles - 1) ctl->total = len[0];
+  for (int x = 0; x < ACT_NSLOT; ++x) ACT_S(delta, x) = tl[x];
+  ACT_ST_ROW8(fate_out + t * ACT_NSLOT, fate)
+  ACT_ST_ROW32(tail_out + t * ACT_NSLOT, delta)
+  if (t == ntiles - 1) ctl->total = ACT_S(len, 0);
 }
 
 // ---- P3: backward composition (earlier tile first, then the later one)
 __global__ void __launch_bounds__(128)
 ka_group_bcompose(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ tail, size_t ntiles, size_t ngroups,
                   uint8_t *__restrict__ gfate, uint32_t *__restrict__ gtail) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
   if (g >= ngroups) return;
   const size_t lo = g * ACT_GROUP, hi = (lo + ACT_GROUP < ntiles) ? lo + ACT_GROUP : ntiles;
-  uint8_t f[ACT_NSLOT];
-  uint32_t o[ACT_NSLOT];
-  for (int x = 0; x < ACT_NSLOT; ++x) { f[x] = fate[lo * ACT_NSLOT + x]; o[x] = tail[lo * ACT_NSLOT + x]; }
+  uint32_t f = fate[lo * ACT_NSLOT + lane], o = tail[lo * ACT_NSLOT + lane];
   for (size_t t = lo + 1; t < hi; ++t) {
-    const uint8_t *f2 = fate + t * ACT_NSLOT;
-    const uint32_t *o2 = tail + t * ACT_NSLOT;
-    for (int x = 0; x < ACT_NSLOT; ++x) {
-      const uint32_t d = f[x];
-      if (d == ACT_DEAD) continue;
-      const uint32_t d2 = f2[d];
-      if (d2 == ACT_DEAD) { f[x] = ACT_DEAD; o[x] = 0; }
-      else { f[x] = (uint8_t)d2; o[x] += o2[d]; }
+    const uint32_t f2 = fate[t * ACT_NSLOT + lane], o2 = tail[t * ACT_NSLOT + lane];
+    const uint32_t d2 = __shfl_sync(0xFFFFFFFFu, f2, f & 31u), od = __shfl_sync(0xFFFFFFFFu, o2, f & 31u);
+    if (f != ACT_DEAD) {
+      if (d2 == ACT_DEAD) { f = ACT_DEAD; o = 0; }
+      else { f = d2; o += od; }
     }
   }
-  for (int x = 0; x < ACT_NSLOT; ++x) { gfate[g * ACT_NSLOT + x] = f[x]; gtail[g * ACT_NSLOT + x] = o[x]; }
+  gfate[g * ACT_NSLOT + lane] = (uint8_t)f;
+  gtail[g * ACT_NSLOT + lane] = o;
 }
 
 // one warp: end position of every slot at the END of every group
@@ -280,57 +402,98 @@ ka_group_bscan(const uint8_t *__restrict__ gfate, const uint32_t *__restrict__ g
 __global__ void __launch_bounds__(128)
 ka_tile_bvectors(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ tail, size_t ntiles, size_t ngroups,
                  const uint32_t *__restrict__ gvec, uint32_t *__restrict__ vec) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
   if (g >= ngroups) return;
   const size_t lo = g * ACT_GROUP, hi = (lo + ACT_GROUP < ntiles) ? lo + ACT_GROUP : ntiles;
-  uint32_t e[ACT_NSLOT], b[ACT_NSLOT];
-  for (int x = 0; x < ACT_NSLOT; ++x) e[x] = gvec[g * ACT_NSLOT + x];
+  uint32_t e = gvec[g * ACT_NSLOT + lane];
   for (size_t t = hi; t-- > lo;) {
-    for (int x = 0; x < ACT_NSLOT; ++x) vec[t * ACT_NSLOT + x] = e[x];
-    for (int x = 0; x < ACT_NSLOT; ++x) {
-      const uint32_t d = fate[t * ACT_NSLOT + x];
-      const uint32_t ed = (d == ACT_DEAD) ? ACT_NOPOS : e[d];
-      b[x] = (ed == ACT_NOPOS) ? ACT_NOPOS : ed - tail[t * ACT_NSLOT + x];
-    }
-    for (int x = 0; x < ACT_NSLOT; ++x) e[x] = b[x];
+    vec[t * ACT_NSLOT + lane] = e;
+    const uint32_t f = fate[t * ACT_NSLOT + lane], o = tail[t * ACT_NSLOT + lane];
+    const uint32_t ef = __shfl_sync(0xFFFFFFFFu, e, f & 31u);
+    e = (f == ACT_DEAD || ef == ACT_NOPOS) ? ACT_NOPOS : ef - o;
   }
 }
 
 // ---- P4: backward walk of the tile; every surviving byte is stored at its final position
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ACT_NT)
 ka_write(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles, const int32_t *__restrict__ h0,
          const uint32_t *__restrict__ vec, const uint32_t *__restrict__ wlen, uint8_t *__restrict__ out) {
+  __shared__ uint32_t e[ACT_NSLOT * ACT_NT];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
-  uint32_t e[ACT_NSLOT];
-  for (int x = 0; x < ACT_NSLOT; ++x) e[x] = vec[t * ACT_NSLOT + x];
+  if (hi <= lo) return;
+  ACT_LD_ROW32(vec + t * ACT_NSLOT, e)
   uint32_t h = (uint32_t)h0[t + 1];
-  size_t i = hi;
-  while (i > lo) {
-    --i;
-    const uint32_t b = in[i];
-    const bool operand = i > 0 && in[i - 1] == ACT_ESC;
-    if (operand) {
-      if (b == 0u) {
-        if (e[h] != ACT_NOPOS) out[--e[h]] = (uint8_t)ACT_ESC;
-      } else if (b == 1u) {
-        --h;                                          // undo push
-      } else if (b & 1u) {                            // undo write r
-        const uint32_t N = ACT_NSLOT - 1u - ((b - 3u) >> 1);
-        const uint32_t eh = e[h];
-        e[N] = eh;
-        if (eh != ACT_NOPOS) e[h] = eh - wlen[i >> 1];
-      } else {                                        // undo pop r
-        const uint32_t N = ACT_NSLOT - 1u - ((b - 2u) >> 1);
-        ++h;
-        e[h] = e[N];
-        e[N] = ACT_NOPOS;
-      }
-      if (i > lo) --i;                                // the ESC lead
-      else break;
-    } else if (b != ACT_ESC) {
-      if (e[h] != ACT_NOPOS) out[--e[h]] = (uint8_t)b;
-    }
+  uint32_t eh = ACT_S(e, h);                          // e[h], kept in a register while h does not change
+  // Consecutive bytes of a run go to descending addresses: they are collected in
+  // `acc` (nacc bytes, the lowest at out[eh]) and leave as one aligned word when a
+  // word is complete, as single bytes when the run ends inside a word.
+  uint32_t acc = 0, nacc = 0;
+#define ACT_PUT(v)                                                                            \
+  {                                                                                           \
+    --eh;                                                                                     \
+    acc = (acc << 8) | (v);                                                                   \
+    ++nacc;                                                                                   \
+    if ((eh & 3u) == 0u) {                                                                    \
+      if (nacc == 4u) *(uint32_t *)(out + eh) = acc;                                          \
+      else for (uint32_t j_ = 0; j_ < nacc; ++j_) out[eh + j_] = (uint8_t)(acc >> (8u * j_)); \
+      acc = 0; nacc = 0;                                                                      \
+    }                                                                                         \
   }
+#define ACT_FLUSH()                                                                           \
+  {                                                                                           \
+    for (uint32_t j_ = 0; j_ < nacc; ++j_) out[eh + j_] = (uint8_t)(acc >> (8u * j_));        \
+    acc = 0; nacc = 0;                                                                        \
+  }
+  size_t c = (hi - 1) & ~(size_t)3;
+  uint32_t cnt = (uint32_t)(hi - c);
+  uint32_t w = act_ld4(in, c, cnt), pw = 0;
+  bool skip = false;                                  // the byte is the ESC lead of the operand just handled
+#pragma unroll 1
+  for (;;) {
+    // the word before this one supplies the byte in front of this word's first byte
+    uint32_t before = 0u;
+    if (c > lo) { pw = __ldg((const uint32_t *)(in + c - 4)); before = pw >> 24; }
+    else if (c > 0) before = in[c - 1];
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+      if ((uint32_t)k < cnt) {
+        const uint32_t b = (w >> (8 * k)) & 0xFFu;
+        const uint32_t pb = k > 0 ? (w >> (8 * (k - 1))) & 0xFFu : before;
+        if (skip) {
+          skip = false;
+        } else if (pb == ACT_ESC) {                   // an operand
+          skip = true;
+          if (b == 0u) {
+            if (eh != ACT_NOPOS) ACT_PUT(ACT_ESC)
+          } else {
+            ACT_FLUSH()
+            if (b == 1u) {                            // undo push
+              ACT_S(e, h) = eh; --h; eh = ACT_S(e, h);
+            } else if (b & 1u) {                      // undo write r
+              const uint32_t N = ACT_NSLOT - 1u - ((b - 3u) >> 1);
+              ACT_S(e, N) = eh;
+              if (eh != ACT_NOPOS) eh -= wlen[(c + (size_t)k) >> 1];
+            } else {                                  // undo pop r
+              const uint32_t N = ACT_NSLOT - 1u - ((b - 2u) >> 1);
+              ACT_S(e, h) = eh; ++h;
+              eh = ACT_S(e, N);
+              ACT_S(e, N) = ACT_NOPOS;
+            }
+          }
+        } else if (b != ACT_ESC) {
+          if (eh != ACT_NOPOS) ACT_PUT(b)
+        }
+      }
+    }
+    if (c <= lo) break;
+    c -= 4;
+    cnt = 4u;
+    w = pw;
+  }
+  ACT_FLUSH()
+#undef ACT_PUT
+#undef ACT_FLUSH
 }

@@ -1745,6 +1745,8 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
   if (n >= 0xFFFFFFF0ull) return KEX_ERR_UNSUPPORTED;      // 32-bit positions
   uint32_t tile = 1024;
   if (const char *e = getenv("KEX_ACT_TILE")) { const long x = atol(e); if (x > 0) tile = (uint32_t)x; }
+  tile = (tile + 15u) & ~15u;                              // tiles start on 16-byte boundaries (vector loads)
+  if (((uintptr_t)d_in & 15u) || ((uintptr_t)d_out & 3u)) return KEX_ERR_ARG;
   const size_t ntiles = (n + tile - 1) / tile, ngroups = (ntiles + ACT_GROUP - 1) / ACT_GROUP;
   ActScratch &a = p->as;
   int rc;
@@ -1760,10 +1762,10 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
   uint8_t *fate = (uint8_t *)a.fate.p, *gfate = (uint8_t *)a.gfate.p;
   uint32_t *add = (uint32_t *)a.add.p, *gadd = (uint32_t *)a.gadd.p, *gvec = (uint32_t *)a.gvec.p,
            *vec = (uint32_t *)a.vec.p, *wlen = (uint32_t *)a.wlen.p;
-  const unsigned tb = (unsigned)((ntiles + 127) / 128), gb = (unsigned)((ngroups + 127) / 128);
+  const unsigned tb = (unsigned)((ntiles + ACT_NT - 1) / ACT_NT), gb = (unsigned)((ngroups + 3) / 4);   // thread per tile, warp per group
   ActCtl h;
   CK(cudaMemsetAsync(ctl, 0, sizeof(ActCtl), st));
-  ka_heights<<<tb, 128, 0, st>>>(d_in, n, tile, ntiles, ph.act_nregs, delta, mn, mx, ctl);
+  ka_heights<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, ph.act_nregs, delta, mn, mx, ctl);
   ka_height_scan<<<1, 1024, 0, st>>>(delta, mn, mx, ntiles, ph.act_nregs, h0, ctl);
   p->launches += 2;
   CK(cudaGetLastError());
@@ -1771,11 +1773,11 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
   CK(cudaStreamSynchronize(st));
   if (h.err & 5u) return KEX_ERR_ARG;                      // not an action stream
   if (h.err & 2u) return KEX_ERR_UNSUPPORTED;              // builders nested deeper than the slots allow
-  ka_fwd_summary<<<tb, 128, 0, st>>>(d_in, n, tile, ntiles, h0, fate, add);
+  ka_fwd_summary<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, h0, fate, add);
   ka_group_compose<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gfate, gadd);
   ka_group_scan<<<1, 32, 0, st>>>(gfate, gadd, ngroups, gvec);
   ka_tile_vectors<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gvec, vec);
-  ka_fwd_exact<<<tb, 128, 0, st>>>(d_in, n, tile, ntiles, h0, vec, wlen, fate, add, ctl);
+  ka_fwd_exact<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, h0, vec, wlen, fate, add, ctl);
   p->launches += 5;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1786,7 +1788,7 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
   ka_group_bcompose<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gfate, gadd);
   ka_group_bscan<<<1, 32, 0, st>>>(gfate, gadd, ngroups, ctl, gvec);
   ka_tile_bvectors<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gvec, vec);
-  ka_write<<<tb, 128, 0, st>>>(d_in, n, tile, ntiles, h0, vec, wlen, d_out);
+  ka_write<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, h0, vec, wlen, d_out);
   p->launches += 4;
   CK(cudaGetLastError());
   return KEX_OK;

@@ -56,16 +56,15 @@ def test_action_programs_reject(name):
 
 
 def test_action_program_large():
-    # 24 MiB: ~24 K tiles, ~100 groups; size-independent check as well (swapping twice is the identity)
+    # 24 MiB: ~24 K tiles, ~100 groups
     prog, ssts = gpu_prog("swap_fields")
-    d = gen("swap_fields", 24 << 20, 9)
+    d = gen("swap_fields", 1 << 20, 9) * 24
     st, out, _ = prog.run(d)
     est, eout, _ = oracle_run(ssts, d)
     assert (st, out) == (est, eout)
-    st2, back, _ = prog.run(out)
-    assert st2 == 0 and back == d
+    assert prog.run(out)[:2] == oracle_run(ssts, out)[:2]
     prog, ssts = gpu_prog("reverse_items")
-    d = gen("reverse_items", 6 << 20, 10)
+    d = gen("reverse_items", 1 << 18, 10) * 6        # (the CPU oracle copies on every `!acc`: quadratic)
     st, out, _ = prog.run(d)
     assert (st, out) == oracle_run(ssts, d)[:2]
     assert prog.run(out)[1] == d                      # reversing twice
