@@ -339,19 +339,28 @@ def compile_kex(src: str, opt: int = 3, with_fast: bool = True, actions: bool = 
     `actions=False` refuses such programs like `--act=false` does."""
     from .frontend.driver import build_ssts
     phases = []
-    s0s = None
+    weaker = {}                      # SSTs at weaker optimisation levels, built on demand
     for s in build_ssts(src, opt, actions=actions):
         if hasattr(s, "nregs"):
             phases.append(s)
             continue
         try:
             phases.append(build_phase(s))
-        except UnsupportedProgram:
-            if opt == 0:
-                raise
-            # constant propagation may move a literal in front of an older
-            # register; the unoptimised SST always has the required shape
-            if s0s is None:
-                s0s = build_ssts(src, 0, actions=actions)
-            phases.append(build_phase(s0s[len(phases)]))
+        except UnsupportedProgram as first:
+            # full constant propagation may move a literal in front of an older register (the
+            # update is then no longer chronological), the unoptimised SST may keep more registers
+            # live than the device holds: try the weak propagation (`--opt 1`, SymbolicSST.hs:323-331),
+            # then none.  I/O behaviour does not depend on --opt.
+            for o in (1, 0):
+                if o >= opt:
+                    continue
+                if o not in weaker:
+                    weaker[o] = build_ssts(src, o, actions=actions)
+                try:
+                    phases.append(build_phase(weaker[o][len(phases)]))
+                    break
+                except UnsupportedProgram:
+                    pass
+            else:
+                raise first
     return serialize_pipeline(phases, with_fast)

@@ -25,6 +25,9 @@ def _phase_headers(blob):
     out = []
     for i in range(n):
         off, ln = struct.unpack_from("<II", blob, 16 + 8 * i)
+        if struct.unpack_from("<I", blob, off)[0] == 0x4158454B:      # action-interpreter phase
+            out.append({"action_registers": struct.unpack_from("<I", blob, off + 8)[0]})
+            continue
         h = struct.unpack_from("<10I", blob, off)
         out.append({"states": h[2], "classes": h[3], "registers": h[4], "actions": h[5],
                     "monoid_section": struct.unpack_from("<I", blob, off + 80)[0] > 0})
@@ -41,6 +44,10 @@ def describe(blob, meta=None):
     ph = _phase_headers(blob)
     lines.append("  phases: %d" % len(ph))
     for i, h in enumerate(ph):
+        if "action_registers" in h:
+            lines.append("  phase %d: action interpreter over the stream of phase %d, %d registers" % (
+                i + 1, i, h["action_registers"]))
+            continue
         lines.append("  phase %d: %d SST states, %d byte classes, %d registers, %d actions, monoid tables: %s" % (
             i + 1, h["states"], h["classes"], h["registers"], h["actions"], "yes" if h["monoid_section"] else "no"))
     return "\n".join(lines) + "\n"

@@ -16,7 +16,7 @@ def test_lockstep_simulator(v):
     assert vec_matches(v, simulate_lockstep(v["program"], v["input"]))
 
 
-@pytest.mark.parametrize("opt", [0, 3])
+@pytest.mark.parametrize("opt", [0, 1, 3])
 @pytest.mark.parametrize("v", [v for v in VECS if not v["uses_registers"]],
                          ids=[v["name"] for v in VECS if not v["uses_registers"]])
 def test_sst_simulator(v, opt):

@@ -110,3 +110,32 @@ def test_launcher_streams_large_inputs(tmp_path):
     w = subprocess.run([out], input=bad, capture_output=True, env=dict(os.environ, KEX_NO_STREAM="1"))
     s2 = subprocess.run([out], input=bad, capture_output=True, env=dict(os.environ, KEX_STREAM_BLOCK_MIB="1"))
     assert w.returncode == s2.returncode == 1 and w.stdout == s2.stdout and w.stderr == s2.stderr
+
+
+def test_action_program_compile_and_simulate(tmp_path):
+    # a program with register actions: refused with --act=false like the reference (Commands.hs:166-168),
+    # two phases per stage with the default --act=true; `simulate --sim=sst` runs both
+    prog = os.path.join(PROGRAMS, "actions", "swap_fields.kex")
+    out = str(tmp_path / "swap")
+    r = subprocess.run(KEXC + ["compile", prog, "--out", out, "--act=false", "--quiet"], capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 1 and b"action symbols" in r.stderr
+    r = subprocess.run(KEXC + ["compile", prog, "--out", out, "--quiet"], capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 0, r.stderr
+    i = subprocess.run([out, "-i"], capture_output=True)
+    assert i.returncode == 2 and b"phases: 2" in i.stdout and b"action interpreter" in i.stdout
+    for sim in ("sst", "lockstep"):
+        s = subprocess.run(KEXC + ["simulate", "--quiet", "--sim=" + sim, prog], input=b"k=v=w\n=\n", capture_output=True,
+                           cwd=ROOT, env=ENV)
+        assert s.returncode == 0 and s.stdout == b"v=w=k\n=\n"
+
+
+@pytest.mark.gpu
+def test_action_program_binary(tmp_path):
+    out = str(tmp_path / "rev")
+    r = subprocess.run(KEXC + ["compile", os.path.join(PROGRAMS, "actions", "reverse_items.kex"), "--out", out, "--quiet"],
+                       capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 0, r.stderr
+    ok = subprocess.run([out], input=b"a;bb;ccc;", capture_output=True)
+    assert ok.returncode == 0 and ok.stdout == b"ccc;bb;a;"
+    bad = subprocess.run([out], input=b"a;bb", capture_output=True)
+    assert bad.returncode == 1 and bad.stderr.startswith(b"Match error at input symbol")

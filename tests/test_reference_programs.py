@@ -14,8 +14,9 @@ from kleenexlang_b200.kexprog import UnsupportedProgram, build_phase
 SRC = "/root/reference/bench/kleenex/src"
 FAST = ["aaa", "as", "csv2json", "csv2json_nows", "csv_project3", "dfamail", "drex_del-comments", "email", "flip_ab",
         "ini2json", "iso_datetime_to_json", "json_project1", "patho2", "rot13", "simple_id", "thousand_sep"]
-# register actions (`reg@t`, `!reg`) reorder or duplicate data: they need the oracle/action mode of the
-# reference and real data movement between registers, which the order-preserving kernels do not do
+# register actions (`reg@t`, `!reg`) reorder or duplicate data: the reference compiles them only in its
+# oracle/action mode; here a stage with actions becomes a transducer phase that writes an action stream
+# plus an action-interpreter phase (frontend/actions.py, csrc/kex_act.cuh)
 ACTIONS = ["dna_regex_noalias_2", "doc_comments", "drex_align-bibtex", "drex_rev-dict", "drex_swap-bibtex",
            "jix_responsetime", "markdown2html", "mitm", "sort_ab", "swap_lines", "worstcase"]
 
@@ -34,6 +35,18 @@ def test_action_programs_are_refused_not_miscompiled(name):
     src = open(os.path.join(SRC, name + ".kex"), encoding="utf-8").read()
     with pytest.raises(ValueError, match="action symbols"):
         build_ssts(src, 3)
+
+
+@pytest.mark.skipif(not os.path.isdir(SRC), reason="reference checkout not present")
+@pytest.mark.parametrize("name", ACTIONS)
+def test_action_programs_compile_as_two_phase_stages(name):
+    from kleenexlang_b200.kexprog import compile_kex, MAGIC_ACT
+    import struct
+    src = open(os.path.join(SRC, name + ".kex"), encoding="utf-8").read()
+    blob = compile_kex(src)
+    nph = struct.unpack_from("<I", blob, 8)[0]
+    magics = [struct.unpack_from("<I", blob, struct.unpack_from("<I", blob, 16 + 8 * i)[0])[0] for i in range(nph)]
+    assert MAGIC_ACT in magics and magics[0] != MAGIC_ACT
 
 
 @pytest.mark.skipif(not os.path.isdir(SRC), reason="reference checkout not present")
