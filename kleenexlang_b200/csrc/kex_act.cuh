@@ -36,7 +36,7 @@
 #define ACT_NSLOT 32
 #define ACT_DEAD 0xFFu
 #define ACT_NOPOS 0xFFFFFFFFu
-#define ACT_GROUP 256u           // tiles composed per group
+#define ACT_GROUP 256u           // tiles composed per group (one warp); the scan over groups is sequential
 
 struct ActCtl {
   uint32_t err;                  // 1 pop on the bottom builder, 2 stack too deep for the slots, 4 register id out of range
@@ -92,57 +92,89 @@ __device__ __forceinline__ uint32_t act_ld4(const uint8_t *__restrict__ in, size
   }
 
 // ---- P0: stack height
+// inclusive scan of one value per thread over a block of ACT_NT threads
+__device__ __forceinline__ long long act_block_scan(long long v, long long *warp_tot, long long &block_total) {
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long y = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if (lane >= (uint32_t)d) v += y;
+  }
+  if (lane == 31u) warp_tot[w] = v;
+  __syncthreads();
+  long long base = 0, tot = 0;
+  for (uint32_t k = 0; k < ACT_NT / 32u; ++k) { if (k < w) base += warp_tot[k]; tot += warp_tot[k]; }
+  block_total = tot;
+  return v + base;
+}
+
+// per tile: net height change, lowest and highest height relative to the tile start; per block: sum of the changes
 __global__ void __launch_bounds__(ACT_NT)
 ka_heights(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles, uint32_t nregs,
-           int32_t *__restrict__ delta, int32_t *__restrict__ mn, int32_t *__restrict__ mx, ActCtl *ctl) {
+           int32_t *__restrict__ delta, int32_t *__restrict__ mn, int32_t *__restrict__ mx,
+           long long *__restrict__ bsum, ActCtl *ctl) {
+  __shared__ long long warp_tot[ACT_NT / 32u];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntiles) return;
-  const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
   int32_t h = 0, l = 0, u = 0;
   bool bad = false;
+  if (t < ntiles) {
+    const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
 #define A_BYTE(i, v)
 #define A_PUSH(i) { ++h; u = h > u ? h : u; }
 #define A_POP(i, r) { --h; l = h < l ? h : l; bad |= (r) >= nregs; }
 #define A_WRITE(i, r) { bad |= (r) >= nregs; }
-  ACT_FWD_TOKENS(in, lo, hi, A_BYTE, A_PUSH, A_POP, A_WRITE)
+    ACT_FWD_TOKENS(in, lo, hi, A_BYTE, A_PUSH, A_POP, A_WRITE)
 #undef A_BYTE
 #undef A_PUSH
 #undef A_POP
 #undef A_WRITE
-  delta[t] = h; mn[t] = l; mx[t] = u;
-  if (bad) atomicOr(&ctl->err, 4u);
+    delta[t] = h; mn[t] = l; mx[t] = u;
+    if (bad) atomicOr(&ctl->err, 4u);
+  }
+  long long tot;
+  act_block_scan((long long)h, warp_tot, tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
 }
 
-// one block: height at the start of every tile, validity
+// one block: exclusive scan of the per-block sums (in place); the height at the end of the stream
 __global__ void __launch_bounds__(1024)
-ka_height_scan(const int32_t *__restrict__ delta, const int32_t *__restrict__ mn, const int32_t *__restrict__ mx,
-               size_t ntiles, uint32_t nregs, int32_t *__restrict__ h0, ActCtl *ctl) {
+ka_height_scan(long long *__restrict__ bsum, size_t nblocks, ActCtl *ctl) {
   __shared__ long long part[1024];
-  const size_t seg = (ntiles + blockDim.x - 1) / blockDim.x;
-  const size_t lo = (size_t)threadIdx.x * seg < ntiles ? (size_t)threadIdx.x * seg : ntiles;
-  const size_t hi = lo + seg < ntiles ? lo + seg : ntiles;
+  const size_t seg = (nblocks + blockDim.x - 1) / blockDim.x;
+  const size_t lo = (size_t)threadIdx.x * seg < nblocks ? (size_t)threadIdx.x * seg : nblocks;
+  const size_t hi = lo + seg < nblocks ? lo + seg : nblocks;
   long long s = 0;
-  for (size_t t = lo; t < hi; ++t) s += delta[t];
+  for (size_t b = lo; b < hi; ++b) s += bsum[b];
   part[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     long long acc = 0;
     for (uint32_t k = 0; k < blockDim.x; ++k) { const long long v = part[k]; part[k] = acc; acc += v; }
+    ctl->hfinal = (int32_t)acc;
   }
   __syncthreads();
   long long h = part[threadIdx.x];
-  long long top = 0;
+  for (size_t b = lo; b < hi; ++b) { const long long v = bsum[b]; bsum[b] = h; h += v; }
+}
+
+// height at the start of every tile (h0[ntiles] = at the end of the stream); validity
+__global__ void __launch_bounds__(ACT_NT)
+ka_tile_heights(const int32_t *__restrict__ delta, const int32_t *__restrict__ mn, const int32_t *__restrict__ mx,
+                const long long *__restrict__ bsum, size_t ntiles, uint32_t nregs, int32_t *__restrict__ h0, ActCtl *ctl) {
+  __shared__ long long warp_tot[ACT_NT / 32u];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long d = (t < ntiles) ? (long long)delta[t] : 0ll;
+  long long tot;
+  const long long incl = act_block_scan(d, warp_tot, tot);
+  if (t >= ntiles) return;
+  const long long h = bsum[blockIdx.x] + incl - d;
+  h0[t] = (int32_t)h;
+  if (t == ntiles - 1) h0[ntiles] = (int32_t)(h + d);
   uint32_t err = 0;
-  for (size_t t = lo; t < hi; ++t) {
-    h0[t] = (int32_t)h;
-    if (h + mn[t] < 0) err |= 1u;
-    if (h + mx[t] > top) top = h + mx[t];
-    h += delta[t];
-  }
-  if (top + 1 + (long long)nregs > ACT_NSLOT) err |= 2u;
-  if (lo < hi && hi == ntiles) { h0[ntiles] = (int32_t)h; ctl->hfinal = (int32_t)h; }
+  if (h + mn[t] < 0) err |= 1u;
+  if (h + mx[t] + 1 + (long long)nregs > ACT_NSLOT) err |= 2u;
   if (err) atomicOr(&ctl->err, err);
-  atomicMax(&ctl->hmax, (int32_t)top);
+  atomicMax(&ctl->hmax, (int32_t)(h + mx[t]));
 }
 
 // ---- slot-content bookkeeping of a tile
@@ -231,10 +263,23 @@ ka_fwd_summary(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t n
 
 // The kernels below run one WARP per group of tiles, lane = slot.
 
+// out[d] = base[d] + sum of v[m] over the slots m with f[m] == d  (lane = slot; `sm` = 32 words of this warp):
+// one shared-memory atomic per lane instead of a 32-step shuffle loop
+__device__ __forceinline__ uint32_t act_scatter_add(uint32_t *sm, uint32_t lane, uint32_t base, uint32_t f, uint32_t v) {
+  sm[lane] = base;
+  __syncwarp();
+  if (f != ACT_DEAD) atomicAdd(&sm[f], v);
+  __syncwarp();
+  const uint32_t r = sm[lane];
+  __syncwarp();
+  return r;
+}
+
 // forward composition of the summaries of one group of tiles (earlier first)
 __global__ void __launch_bounds__(128)
 ka_group_compose(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ add, size_t ntiles, size_t ngroups,
                  uint8_t *__restrict__ gfate, uint32_t *__restrict__ gadd) {
+  __shared__ uint32_t sm[4][32];
   const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (g >= ngroups) return;
@@ -242,12 +287,7 @@ ka_group_compose(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ 
   uint32_t f = fate[lo * ACT_NSLOT + lane], a = add[lo * ACT_NSLOT + lane];
   for (size_t t = lo + 1; t < hi; ++t) {
     const uint32_t f2 = fate[t * ACT_NSLOT + lane];
-    uint32_t acc = add[t * ACT_NSLOT + lane];
-#pragma unroll
-    for (int m = 0; m < ACT_NSLOT; ++m) {
-      const uint32_t fm = __shfl_sync(0xFFFFFFFFu, f2, m), am = __shfl_sync(0xFFFFFFFFu, a, m);
-      if (fm == lane) acc += am;
-    }
+    const uint32_t acc = act_scatter_add(sm[threadIdx.x >> 5], lane, add[t * ACT_NSLOT + lane], f2, a);
     const uint32_t nf = __shfl_sync(0xFFFFFFFFu, f2, f & 31u);
     f = (f == ACT_DEAD) ? ACT_DEAD : nf;
     a = acc;
@@ -260,6 +300,7 @@ ka_group_compose(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ 
 __global__ void __launch_bounds__(32)
 ka_group_scan(const uint8_t *__restrict__ gfate, const uint32_t *__restrict__ gadd, size_t ngroups,
               uint32_t *__restrict__ gvec) {
+  __shared__ uint32_t sm[32];
   const uint32_t lane = threadIdx.x;
   uint32_t v = 0;
   uint32_t f = ngroups ? gfate[lane] : 0u, acc = ngroups ? gadd[lane] : 0u;
@@ -268,12 +309,7 @@ ka_group_scan(const uint8_t *__restrict__ gfate, const uint32_t *__restrict__ ga
     // the next group's summary is loaded before this one's dependent arithmetic
     const uint32_t nf = (g + 1 < ngroups) ? gfate[(g + 1) * ACT_NSLOT + lane] : 0u;
     const uint32_t na = (g + 1 < ngroups) ? gadd[(g + 1) * ACT_NSLOT + lane] : 0u;
-#pragma unroll
-    for (int m = 0; m < ACT_NSLOT; ++m) {
-      const uint32_t fm = __shfl_sync(0xFFFFFFFFu, f, m), vm = __shfl_sync(0xFFFFFFFFu, v, m);
-      if (fm == lane) acc += vm;
-    }
-    v = acc;
+    v = act_scatter_add(sm, lane, acc, f, v);
     f = nf;
     acc = na;
   }
@@ -284,6 +320,7 @@ ka_group_scan(const uint8_t *__restrict__ gfate, const uint32_t *__restrict__ ga
 __global__ void __launch_bounds__(128)
 ka_tile_vectors(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ add, size_t ntiles, size_t ngroups,
                 const uint32_t *__restrict__ gvec, uint32_t *__restrict__ vec) {
+  __shared__ uint32_t sm[4][32];
   const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (g >= ngroups) return;
@@ -291,14 +328,7 @@ ka_tile_vectors(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ a
   uint32_t v = gvec[g * ACT_NSLOT + lane];
   for (size_t t = lo; t < hi; ++t) {
     vec[t * ACT_NSLOT + lane] = v;
-    const uint32_t f = fate[t * ACT_NSLOT + lane];
-    uint32_t acc = add[t * ACT_NSLOT + lane];
-#pragma unroll
-    for (int m = 0; m < ACT_NSLOT; ++m) {
-      const uint32_t fm = __shfl_sync(0xFFFFFFFFu, f, m), vm = __shfl_sync(0xFFFFFFFFu, v, m);
-      if (fm == lane) acc += vm;
-    }
-    v = acc;
+    v = act_scatter_add(sm[threadIdx.x >> 5], lane, add[t * ACT_NSLOT + lane], fate[t * ACT_NSLOT + lane], v);
   }
 }
 

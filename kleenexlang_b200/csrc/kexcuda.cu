@@ -673,7 +673,7 @@ struct Buf {
 
 // scratch of the action-interpreter kernels
 struct ActScratch {
-  Buf delta, mn, mx, h0, fate, add, gfate, gadd, gvec, vec, wlen, ctl;
+  Buf delta, mn, mx, h0, bsum, fate, add, gfate, gadd, gvec, vec, wlen, ctl;
 };
 
 // Scratch of one run / shard in flight (grow-only device buffers and the state
@@ -1136,7 +1136,7 @@ extern "C" void kex_free(kex_program *p) {
   for (Buf *b : {&p->inter[0], &p->inter[1], &p->hostio_in, &p->hostio_out, &p->sin[0], &p->sin[1], &p->sout}) cudaFree(b->p);
   {
     ActScratch &a = p->as;
-    Buf *abs[] = {&a.delta, &a.mn, &a.mx, &a.h0, &a.fate, &a.add, &a.gfate, &a.gadd, &a.gvec, &a.vec, &a.wlen, &a.ctl};
+    Buf *abs[] = {&a.delta, &a.mn, &a.mx, &a.h0, &a.bsum, &a.fate, &a.add, &a.gfate, &a.gadd, &a.gvec, &a.vec, &a.wlen, &a.ctl};
     for (Buf *b : abs) cudaFree(b->p);
   }
   if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
@@ -1751,7 +1751,7 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
   ActScratch &a = p->as;
   int rc;
   if ((rc = ensure(p, a.delta, 4 * ntiles)) || (rc = ensure(p, a.mn, 4 * ntiles)) || (rc = ensure(p, a.mx, 4 * ntiles)) ||
-      (rc = ensure(p, a.h0, 4 * (ntiles + 1))) || (rc = ensure(p, a.fate, (size_t)ACT_NSLOT * ntiles)) ||
+      (rc = ensure(p, a.h0, 4 * (ntiles + 1))) || (rc = ensure(p, a.bsum, 8 * ((ntiles + ACT_NT - 1) / ACT_NT + 1))) || (rc = ensure(p, a.fate, (size_t)ACT_NSLOT * ntiles)) ||
       (rc = ensure(p, a.add, 4ull * ACT_NSLOT * ntiles)) || (rc = ensure(p, a.gfate, (size_t)ACT_NSLOT * ngroups)) ||
       (rc = ensure(p, a.gadd, 4ull * ACT_NSLOT * ngroups)) || (rc = ensure(p, a.gvec, 4ull * ACT_NSLOT * (ngroups + 1))) ||
       (rc = ensure(p, a.vec, 4ull * ACT_NSLOT * ntiles)) || (rc = ensure(p, a.wlen, 4ull * (n / 2 + 1))) ||
@@ -1765,9 +1765,11 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
   const unsigned tb = (unsigned)((ntiles + ACT_NT - 1) / ACT_NT), gb = (unsigned)((ngroups + 3) / 4);   // thread per tile, warp per group
   ActCtl h;
   CK(cudaMemsetAsync(ctl, 0, sizeof(ActCtl), st));
-  ka_heights<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, ph.act_nregs, delta, mn, mx, ctl);
-  ka_height_scan<<<1, 1024, 0, st>>>(delta, mn, mx, ntiles, ph.act_nregs, h0, ctl);
-  p->launches += 2;
+  long long *bsum = (long long *)a.bsum.p;
+  ka_heights<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, ph.act_nregs, delta, mn, mx, bsum, ctl);
+  ka_height_scan<<<1, 1024, 0, st>>>(bsum, tb, ctl);
+  ka_tile_heights<<<tb, ACT_NT, 0, st>>>(delta, mn, mx, bsum, ntiles, ph.act_nregs, h0, ctl);
+  p->launches += 3;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
