@@ -13,6 +13,18 @@
  * `kexprog` blob (kleenexlang_b200/kexprog.py documents the layout) and the
  * launcher hands the blob and the input bytes to this library.
  *
+ * A stage with register actions (`reg@t`, `!reg`: what compileOracleAction,
+ * src/KMC/Frontend/Commands.hs:204-244, compiles to an oracle/action pair)
+ * occupies two phases of a blob as well: a transducer phase whose output is an
+ * action stream and an action-interpreter phase (the register effects of
+ * src/KMC/SymbolicSST/ActionSST.hs:83-104; kleenexlang_b200/csrc/kex_act.cuh).
+ * kex_run_host / kex_run_device / kex_select_phase / kex_info / kex_out_bound
+ * handle such blobs; the sharded and block-streaming entry points answer
+ * KEX_ERR_UNSUPPORTED (they require a single-phase program anyway).  A stream
+ * that is not an action stream (pop on the bottom builder, unknown register)
+ * gives KEX_ERR_ARG, builders nested deeper than 32 - registers
+ * KEX_ERR_UNSUPPORTED.
+ *
  * Plain pointers and sizes only.  All functions return KEX_OK (0) or a
  * negative KEX_ERR_* code; nothing is printed and nothing calls exit().
  */
