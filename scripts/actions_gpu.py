@@ -19,6 +19,12 @@ for name in names:
         torch.cuda.synchronize(); t0 = time.perf_counter()
         st, olen, _ = prog.run_device(d_in.data_ptr(), n, d_out.data_ptr(), d_out.numel())
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    # size-independent check: every program here works record by record (or reverses a list of
+    # records), so the output of `reps` copies of the block is `reps` copies of the block's output
+    bo = prog.run(block.tobytes())
+    ok = bo[0] == 0 and olen == len(bo[1]) * reps and bool(
+        (d_out[:olen].view(reps, len(bo[1])) == torch.frombuffer(bytearray(bo[1]), dtype=torch.uint8).cuda()).all())
+    print("   verified against %d x the block's output: %s" % (reps, "OK" if ok else "MISMATCH"), flush=True)
     prog.select_phase(1)
     d_mid = torch.empty(int(n * 14) + (1 << 20), dtype=torch.uint8, device="cuda")
     for i in range(2):
