@@ -5,7 +5,7 @@ Mirrors `createProgram` / `buildTransducers` / `generateDirectSSTs`
 configuration: parse, desugar, one transducer per pipeline stage, path-tree
 determinization, optional constant-propagation optimisation.
 """
-from .kleenex import parse_kleenex, desugar
+from .kleenex import parse_kleenex, desugar, check_well_formedness
 from .fst import construct_transducer, run_lockstep, run_actions
 from .sst import sst_from_fst, optimize, run_sst
 from .actions import ActStage, action_stream_fst, run_act_stream
@@ -13,6 +13,7 @@ from .actions import ActStage, action_stream_fst, run_act_stream
 
 def build_transducers(src: str):
     pipeline, decls = parse_kleenex(src)
+    check_well_formedness(pipeline, decls)
     pl, rdecls = desugar(pipeline, decls)
     return [construct_transducer(rdecls, ident) for ident in pl]
 

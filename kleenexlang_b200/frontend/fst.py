@@ -38,6 +38,10 @@ class FST:
         return False
 
 
+MAX_FST_STATES = 2000000
+MAX_STACK_DEPTH = 4096          # continuation stacks of well-formed grammars are as deep as the definitions nest
+
+
 def construct_transducer(decls, initial):
     """constructTransducer (Transducer.hs:57-107)."""
 
@@ -61,6 +65,11 @@ def construct_transducer(decls, initial):
         if q in states:
             continue
         states.add(q)
+        if len(states) > MAX_FST_STATES or len(q) > MAX_STACK_DEPTH:
+            # only reachable for self-embedding grammars that slip through the (restated) check, e.g. a
+            # recursive call in tail position of a starred term: the reference builds states forever there
+            raise ValueError("transducer construction does not terminate: the grammar is self-embedding "
+                             "(continuation stack deeper than %d or more than %d states)" % (MAX_STACK_DEPTH, MAX_FST_STATES))
         if not q:
             continue
         d = decls[q[0]]

@@ -450,6 +450,127 @@ class _Desugar:
         raise KleenexSyntaxError("unknown term %r" % (k,))
 
 
+# ------------------------------------------------------------ well-formedness
+class KleenexWellFormednessError(KleenexSyntaxError):
+    pass
+
+
+_WRAPPERS = {"star": 1, "plus": 1, "question": 1, "suppress": 1, "range": 3, "redirect": 2}
+
+
+def _term_idents(t):
+    """All nonterminals occurring in a term (`termIdents`, WellFormedness.hs:98-112)."""
+    k = t[0]
+    if k == "var":
+        return {t[1]}
+    if k in ("seq", "sum"):
+        out = set()
+        for x in t[1]:
+            out |= _term_idents(x)
+        return out
+    if k in _WRAPPERS:
+        return _term_idents(t[_WRAPPERS[k]])
+    return set()
+
+
+def _strict_deps(t):
+    """Nonterminals in strict (non-tail) positions (`strictDeps`, WellFormedness.hs:115-128)."""
+    k = t[0]
+    if k == "seq":
+        out = set()
+        for x in t[1][:-1]:
+            out |= _term_idents(x)
+        return out | (_strict_deps(t[1][-1]) if t[1] else set())
+    if k == "sum":
+        out = set()
+        for x in t[1]:
+            out |= _strict_deps(x)
+        return out
+    if k in _WRAPPERS:
+        return _strict_deps(t[_WRAPPERS[k]])
+    return set()
+
+
+def _succs(name, t):
+    """`succs` (WellFormedness.hs:81-95): star and plus make the declaration self-referential."""
+    k = t[0]
+    if k == "var":
+        return {t[1]}
+    if k in ("seq", "sum"):
+        out = set()
+        for x in t[1]:
+            out |= _succs(name, x)
+        return out
+    if k in ("star", "plus"):
+        return {name} | _succs(name, t[1])
+    if k in _WRAPPERS:
+        return _succs(name, t[_WRAPPERS[k]])
+    return set()
+
+
+def check_well_formedness(pipeline, decls):
+    """`checkWellFormedness` (WellFormedness.hs:205-243): no nonterminal declared twice, the pipeline only
+    names declared nonterminals, and the grammar is non-self-embedding -- no strongly connected component of
+    the dependency graph contains a strict (non-tail) occurrence of one of its own members.  Without the last
+    property the transducer's states (continuation stacks, Transducer.hs:57-107) are unbounded."""
+    declmap = {}
+    for name, t in decls:
+        if name in declmap:
+            raise KleenexWellFormednessError("Error: Multiple declarations of nonterminal '%s'." % name)
+        declmap[name] = t
+    if not pipeline:
+        raise KleenexWellFormednessError("Error: Empty pipeline")
+    undecl = [n for n in pipeline if n not in declmap]
+    if undecl:
+        raise KleenexWellFormednessError("Error: Undeclared nonterminals in pipeline: " + ", ".join(undecl))
+    graph = {n: sorted(x for x in _succs(n, t) if x in declmap) for n, t in declmap.items()}
+    # Tarjan's strongly connected components, iterative
+    index, low, on, stack, comps = {}, {}, set(), [], []
+    for root in sorted(graph):
+        if root in index:
+            continue
+        work = [(root, 0)]
+        while work:
+            v, i = work.pop()
+            if i == 0:
+                index[v] = low[v] = len(index)
+                stack.append(v)
+                on.add(v)
+            recurse = False
+            for j in range(i, len(graph[v])):
+                w = graph[v][j]
+                if w not in index:
+                    work.append((v, j + 1))
+                    work.append((w, 0))
+                    recurse = True
+                    break
+                if w in on:
+                    low[v] = min(low[v], index[w])
+            if recurse:
+                continue
+            if low[v] == index[v]:
+                comp = set()
+                while True:
+                    w = stack.pop()
+                    on.discard(w)
+                    comp.add(w)
+                    if w == v:
+                        break
+                comps.append(comp)
+            if work:
+                u = work[-1][0]
+                low[u] = min(low[u], low[v])
+    for comp in comps:
+        for name in sorted(comp):
+            bad = sorted(_strict_deps(declmap[name]) & comp)
+            if bad:
+                raise KleenexWellFormednessError(
+                    "Error: Strict occurrences in mutually recursive definition of '%s' involving nonterminals %s. "
+                    "Occurrences: %s" % (name, ", ".join("'%s'" % c for c in sorted(comp)),
+                                         ", ".join("'%s'" % b for b in bad)))
+    return comps
+
+
 def desugar(pipeline, decls):
     """desugarProg (Desugaring.hs:180-212) -> (pipeline ids, {id: reduced term})."""
     names = [n for n, _ in decls]

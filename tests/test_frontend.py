@@ -61,3 +61,28 @@ def test_csv2json_sample():
 def test_state_counts_stable():
     s = build_ssts(program_source("csv2json"))[0]
     assert (s.nstates, len(s.edges)) == (27, 27)
+
+
+def test_well_formedness():
+    # checkWellFormedness (src/KMC/Kleenex/WellFormedness.hs:205-243)
+    from kleenexlang_b200.frontend.driver import build_transducers
+    from kleenexlang_b200.frontend.kleenex import KleenexWellFormednessError
+    for src, what in [('main := /a/ main /b/ | ""', "Strict occurrences"),
+                      ('main := a\na := /x/ b /y/ | ""\nb := a', "Strict occurrences"),
+                      ('main := /a/\nmain := /b/', "Multiple declarations"),
+                      ('start: foo\nmain := /a/', "Undeclared nonterminals")]:
+        with pytest.raises(KleenexWellFormednessError, match=what):
+            build_transducers(src)
+    # tail recursion and recursion through other nonterminals are fine
+    assert len(build_transducers('main := /a/ main | ""')[0].states) == 4
+    assert build_transducers('main := a*\na := /x/ b\nb := /y/ | /z/ b')
+    # the reference's check lets a tail call inside a starred term through and then builds states forever;
+    # here the construction gives up
+    with pytest.raises(ValueError, match="self-embedding"):
+        build_transducers('main := (/a/ | "b" main)*')
+
+
+@pytest.mark.parametrize("name", ["csv2json", "iso_datetime_to_json", "thousand_sep", "add-commas", "fastq2fasta", "apache_log"])
+def test_bundled_programs_are_well_formed(name):
+    from kleenexlang_b200.frontend.kleenex import check_well_formedness
+    assert check_well_formedness(*parse_kleenex(program_source(name)))

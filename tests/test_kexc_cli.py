@@ -139,3 +139,14 @@ def test_action_program_binary(tmp_path):
     assert ok.returncode == 0 and ok.stdout == b"ccc;bb;a;"
     bad = subprocess.run([out], input=b"a;bb", capture_output=True)
     assert bad.returncode == 1 and bad.stderr.startswith(b"Match error at input symbol")
+
+
+def test_malformed_programs_exit_with_a_message(tmp_path):
+    # parse errors and self-embedding grammars (WellFormedness.hs:205-243) are reported, exit status 1
+    for k, (text, msg) in enumerate([('main := /a/ main /b/ | ""\n', b"Strict occurrences"), ("main := /a\n", b"expected"),
+                                     ("main := /a/\nmain := /b/\n", b"Multiple declarations")]):
+        src = tmp_path / ("m%d.kex" % k)
+        src.write_text(text, encoding="utf-8")
+        r = subprocess.run(KEXC + ["compile", str(src), "--out", str(tmp_path / "o"), "--quiet"], capture_output=True,
+                           cwd=ROOT, env=ENV)
+        assert r.returncode == 1 and msg in r.stderr and b"Traceback" not in r.stderr
