@@ -129,3 +129,26 @@ def test_reference_bench_programs_with_actions(name):
     ssts = build_ssts(src, 3, actions=True)
     assert oracle_run(ssts, data)[:2] == (0, exp)
     compile_kex(src)
+
+
+def load_action_vectors():
+    import base64
+    import json
+    from conftest import GOLDEN
+    vecs = json.load(open(os.path.join(GOLDEN, "action_vectors.json")))
+    for v in vecs:
+        v["input"] = base64.b64decode(v["input"])
+        v["output"] = base64.b64decode(v["output"])
+    return vecs
+
+
+def test_committed_action_vectors():
+    # tests/golden/action_vectors.json (scripts/gen_action_vectors.py: lockstep simulation + Actions.hs semantics)
+    ssts = {}
+    for v in load_action_vectors():
+        if v["program"] not in ssts:
+            ssts[v["program"]] = build_ssts(source(v["program"]), 3, actions=True)
+        st, out, _ = oracle_run(ssts[v["program"]], v["input"])
+        assert (st == 0) == v["accept"]
+        if v["accept"]:
+            assert out == v["output"]

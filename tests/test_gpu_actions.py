@@ -97,3 +97,13 @@ def test_interpreter_refuses_what_it_cannot_hold():
         prog.run(bytes([ESC, 1]) * 40)                 # 40 nested builders > 32 slots
     with pytest.raises(KexError):
         prog.run(bytes([ESC, 3 + 2 * 7]))              # register 7 of 2
+
+
+def test_committed_action_vectors_on_gpu():
+    from test_actions import load_action_vectors
+    for v in load_action_vectors():
+        prog, _ = gpu_prog(v["program"])
+        st, out, _ = prog.run(v["input"])
+        assert (st == 0) == v["accept"], v["program"]
+        if v["accept"]:
+            assert out == v["output"], v["program"]
