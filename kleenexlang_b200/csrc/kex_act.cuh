@@ -461,6 +461,10 @@ ka_write(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles,
   // `acc` (nacc bytes, the lowest at out[eh]) and leave as one aligned word when a
   // word is complete, as single bytes when the run ends inside a word.
   uint32_t acc = 0, nacc = 0;
+#ifdef ACT_BYTE_STORES          // plain byte stores, kept for comparison: 30.7 vs 33.4 GiB/s on swap_fields
+#define ACT_PUT(v) { out[--eh] = (uint8_t)(v); }
+#define ACT_FLUSH() {}
+#else
 #define ACT_PUT(v)                                                                            \
   {                                                                                           \
     --eh;                                                                                     \
@@ -477,6 +481,7 @@ ka_write(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles,
     for (uint32_t j_ = 0; j_ < nacc; ++j_) out[eh + j_] = (uint8_t)(acc >> (8u * j_));        \
     acc = 0; nacc = 0;                                                                        \
   }
+#endif
   size_t c = (hi - 1) & ~(size_t)3;
   uint32_t cnt = (uint32_t)(hi - c);
   uint32_t w = act_ld4(in, c, cnt), pw = 0;
