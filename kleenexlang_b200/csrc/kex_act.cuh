@@ -189,9 +189,9 @@ ka_tile_heights(const int32_t *__restrict__ delta, const int32_t *__restrict__ m
 // fate[x] = slot the old content x ended up in (ACT_DEAD: dropped); `sor` is scratch.
 #define ACT_FATES(root, parent, sor, fate)                                                    \
   {                                                                                           \
-    for (int x_ = 0; x_ < ACT_NSLOT; ++x_) ACT_S(sor, x_) = (uint8_t)ACT_DEAD;                \
-    for (int d_ = 0; d_ < ACT_NSLOT; ++d_) { const uint32_t r_ = ACT_S(root, d_); if (r_ != ACT_DEAD) ACT_S(sor, r_) = (uint8_t)d_; } \
-    for (int x_ = 0; x_ < ACT_NSLOT; ++x_) {                                                  \
+    for (uint32_t x_ = 0; x_ < nslots; ++x_) ACT_S(sor, x_) = (uint8_t)ACT_DEAD;              \
+    for (uint32_t d_ = 0; d_ < nslots; ++d_) { const uint32_t r_ = ACT_S(root, d_); if (r_ != ACT_DEAD) ACT_S(sor, r_) = (uint8_t)d_; } \
+    for (uint32_t x_ = 0; x_ < nslots; ++x_) {                                                \
       uint32_t r_ = (uint32_t)x_;                                                             \
       for (;;) { const uint32_t p_ = ACT_S(parent, r_); if (p_ == ACT_DEAD) break; r_ = p_; } \
       ACT_S(fate, x_) = ACT_S(sor, r_);                                                       \
@@ -200,49 +200,73 @@ ka_tile_heights(const int32_t *__restrict__ delta, const int32_t *__restrict__ m
 
 // A thread's row of a per-tile table is contiguous (32 B of fates, 128 B of
 // lengths): whole-sector vector accesses.
+// (only the first `nslots` slots are in use: slot h < nslots - registers = builder at height h, slot
+// nslots-1-r = register r; the unused entries of a row are DEAD / 0 so that the warp kernels, lane = slot,
+// need not know)
 #define ACT_ST_ROW8(dst, arr)                                                                 \
   {                                                                                           \
     uint32_t w_[8];                                                                           \
     _Pragma("unroll")                                                                         \
-    for (int k_ = 0; k_ < 8; ++k_)                                                            \
-      w_[k_] = (uint32_t)ACT_S(arr, 4 * k_) | ((uint32_t)ACT_S(arr, 4 * k_ + 1) << 8) |       \
-               ((uint32_t)ACT_S(arr, 4 * k_ + 2) << 16) | ((uint32_t)ACT_S(arr, 4 * k_ + 3) << 24); \
+    for (uint32_t k_ = 0; k_ < 8u; ++k_) {                                                    \
+      uint32_t v_ = 0xFFFFFFFFu;                                                              \
+      if (4u * k_ < nslots) {                                                                 \
+        v_ = 0u;                                                                              \
+        _Pragma("unroll")                                                                     \
+        for (uint32_t j_ = 0; j_ < 4u; ++j_)                                                  \
+          v_ |= (4u * k_ + j_ < nslots ? (uint32_t)ACT_S(arr, 4u * k_ + j_) : 0xFFu) << (8u * j_); \
+      }                                                                                       \
+      w_[k_] = v_;                                                                            \
+    }                                                                                         \
     ((uint4 *)(dst))[0] = make_uint4(w_[0], w_[1], w_[2], w_[3]);                             \
     ((uint4 *)(dst))[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                             \
   }
 #define ACT_ST_ROW32(dst, arr)                                                                \
   {                                                                                           \
     _Pragma("unroll")                                                                         \
-    for (int k_ = 0; k_ < 8; ++k_)                                                            \
-      ((uint4 *)(dst))[k_] = make_uint4(ACT_S(arr, 4 * k_), ACT_S(arr, 4 * k_ + 1), ACT_S(arr, 4 * k_ + 2), ACT_S(arr, 4 * k_ + 3)); \
+    for (uint32_t k_ = 0; k_ < 8u; ++k_) {                                                    \
+      uint4 q_ = make_uint4(0u, 0u, 0u, 0u);                                                  \
+      if (4u * k_ < nslots) {                                                                 \
+        q_.x = ACT_S(arr, 4u * k_);                                                           \
+        if (4u * k_ + 1u < nslots) q_.y = ACT_S(arr, 4u * k_ + 1u);                           \
+        if (4u * k_ + 2u < nslots) q_.z = ACT_S(arr, 4u * k_ + 2u);                           \
+        if (4u * k_ + 3u < nslots) q_.w = ACT_S(arr, 4u * k_ + 3u);                           \
+      }                                                                                       \
+      ((uint4 *)(dst))[k_] = q_;                                                              \
+    }                                                                                         \
   }
 #define ACT_LD_ROW32(src, arr)                                                                \
   {                                                                                           \
-    _Pragma("unroll")                                                                         \
-    for (int k_ = 0; k_ < 8; ++k_) {                                                          \
+    for (uint32_t k_ = 0; 4u * k_ < nslots; ++k_) {                                           \
       const uint4 q_ = ((const uint4 *)(src))[k_];                                            \
-      ACT_S(arr, 4 * k_) = q_.x; ACT_S(arr, 4 * k_ + 1) = q_.y; ACT_S(arr, 4 * k_ + 2) = q_.z; ACT_S(arr, 4 * k_ + 3) = q_.w; \
+      ACT_S(arr, 4u * k_) = q_.x;                                                             \
+      if (4u * k_ + 1u < nslots) ACT_S(arr, 4u * k_ + 1u) = q_.y;                             \
+      if (4u * k_ + 2u < nslots) ACT_S(arr, 4u * k_ + 2u) = q_.z;                             \
+      if (4u * k_ + 3u < nslots) ACT_S(arr, 4u * k_ + 3u) = q_.w;                             \
     }                                                                                         \
   }
+
+extern __shared__ __align__(16) uint32_t act_sm[];
 
 // ---- P1: forward summary of a tile (fate of every slot's old content, bytes added per slot)
 __global__ void __launch_bounds__(ACT_NT)
 ka_fwd_summary(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles,
-               const int32_t *__restrict__ h0, uint8_t *__restrict__ fate_out, uint32_t *__restrict__ add_out) {
-  __shared__ uint32_t add[ACT_NSLOT * ACT_NT];
-  __shared__ uint8_t root[ACT_NSLOT * ACT_NT], parent[ACT_NSLOT * ACT_NT], sor[ACT_NSLOT * ACT_NT], fate[ACT_NSLOT * ACT_NT];
+               const int32_t *__restrict__ h0, uint32_t nslots, uint8_t *__restrict__ fate_out,
+               uint32_t *__restrict__ add_out) {
+  uint32_t *add = act_sm;                                        // dynamic shared memory: nslots * ACT_NT * (4 + 4 x 1) bytes
+  uint8_t *root = (uint8_t *)(add + nslots * ACT_NT), *parent = root + nslots * ACT_NT, *sor = parent + nslots * ACT_NT,
+          *fate = sor + nslots * ACT_NT;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
-  for (int x = 0; x < ACT_NSLOT; ++x) { ACT_S(add, x) = 0; ACT_S(root, x) = (uint8_t)x; ACT_S(parent, x) = (uint8_t)ACT_DEAD; }
+  for (uint32_t x = 0; x < nslots; ++x) { ACT_S(add, x) = 0; ACT_S(root, x) = (uint8_t)x; ACT_S(parent, x) = (uint8_t)ACT_DEAD; }
   uint32_t h = (uint32_t)h0[t];
   uint32_t cur = 0;                                 // add[h], kept in a register while h does not change
 #define A_BYTE(i, v) { cur += 1u; }
 #define A_PUSH(i) { ACT_S(add, h) = cur; ++h; cur = ACT_S(add, h); }
-#define A_POP(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r);                                \
+#define A_POP(i, r) { const uint32_t N = nslots - 1u - (r);                                \
     ACT_S(root, N) = ACT_S(root, h); ACT_S(root, h) = (uint8_t)ACT_DEAD;                      \
     ACT_S(add, N) = cur; ACT_S(add, h) = 0; --h; cur = ACT_S(add, h); }
-#define A_WRITE(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r);                              \
+#define A_WRITE(i, r) { const uint32_t N = nslots - 1u - (r);                              \
     const uint32_t rN = ACT_S(root, N);                                                       \
     if (rN != ACT_DEAD) {                                                                     \
       const uint32_t rh = ACT_S(root, h);                                                     \
@@ -336,23 +360,24 @@ ka_tile_vectors(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ a
 // (fate as in P1; tail = bytes behind a slot's old content inside the slot it ended up in)
 __global__ void __launch_bounds__(ACT_NT)
 ka_fwd_exact(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles, const int32_t *__restrict__ h0,
-             const uint32_t *__restrict__ vec, uint32_t *__restrict__ wlen, uint8_t *__restrict__ fate_out,
-             uint32_t *__restrict__ tail_out, ActCtl *ctl) {
-  __shared__ uint32_t len[ACT_NSLOT * ACT_NT], delta[ACT_NSLOT * ACT_NT];
-  __shared__ uint8_t root[ACT_NSLOT * ACT_NT], parent[ACT_NSLOT * ACT_NT], sor[ACT_NSLOT * ACT_NT], fate[ACT_NSLOT * ACT_NT];
+             uint32_t nslots, const uint32_t *__restrict__ vec, uint32_t *__restrict__ wlen,
+             uint8_t *__restrict__ fate_out, uint32_t *__restrict__ tail_out, ActCtl *ctl) {
+  uint32_t *len = act_sm, *delta = len + nslots * ACT_NT;        // dynamic shared memory: nslots * ACT_NT * (8 + 4 x 1) bytes
+  uint8_t *root = (uint8_t *)(delta + nslots * ACT_NT), *parent = root + nslots * ACT_NT, *sor = parent + nslots * ACT_NT,
+          *fate = sor + nslots * ACT_NT;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
   ACT_LD_ROW32(vec + t * ACT_NSLOT, len)
-  for (int x = 0; x < ACT_NSLOT; ++x) { ACT_S(delta, x) = 0; ACT_S(root, x) = (uint8_t)x; ACT_S(parent, x) = (uint8_t)ACT_DEAD; }
+  for (uint32_t x = 0; x < nslots; ++x) { ACT_S(delta, x) = 0; ACT_S(root, x) = (uint8_t)x; ACT_S(parent, x) = (uint8_t)ACT_DEAD; }
   uint32_t h = (uint32_t)h0[t];
   uint32_t cur = ACT_S(len, h);                     // len[h], kept in a register while h does not change
 #define A_BYTE(i, v) { cur += 1u; }
 #define A_PUSH(i) { ACT_S(len, h) = cur; ++h; cur = ACT_S(len, h); }
-#define A_POP(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r);                                \
+#define A_POP(i, r) { const uint32_t N = nslots - 1u - (r);                                \
     ACT_S(root, N) = ACT_S(root, h); ACT_S(root, h) = (uint8_t)ACT_DEAD;                      \
     ACT_S(len, N) = cur; ACT_S(len, h) = 0; --h; cur = ACT_S(len, h); }
-#define A_WRITE(i, r) { const uint32_t N = ACT_NSLOT - 1u - (r);                              \
+#define A_WRITE(i, r) { const uint32_t N = nslots - 1u - (r);                              \
     const uint32_t ln_ = ACT_S(len, N);                                                       \
     wlen[(i) >> 1] = ln_;                                                                     \
     const uint32_t rN = ACT_S(root, N);                                                       \
@@ -376,7 +401,7 @@ ka_fwd_exact(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t nti
   uint32_t tl[ACT_NSLOT];
   const uint32_t *len0 = vec + t * ACT_NSLOT;
 #pragma unroll 1
-  for (int x = 0; x < ACT_NSLOT; ++x) {
+  for (uint32_t x = 0; x < nslots; ++x) {
     const uint32_t d = ACT_S(fate, x);
     uint32_t endoff = len0[x], r = (uint32_t)x;
     for (;;) {
@@ -387,7 +412,7 @@ ka_fwd_exact(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t nti
     }
     tl[x] = (d == ACT_DEAD) ? 0u : ACT_S(len, d) - endoff;
   }
-  for (int x = 0; x < ACT_NSLOT; ++x) ACT_S(delta, x) = tl[x];
+  for (uint32_t x = 0; x < nslots; ++x) ACT_S(delta, x) = tl[x];
   ACT_ST_ROW8(fate_out + t * ACT_NSLOT, fate)
   ACT_ST_ROW32(tail_out + t * ACT_NSLOT, delta)
   if (t == ntiles - 1) ctl->total = ACT_S(len, 0);
@@ -448,8 +473,9 @@ ka_tile_bvectors(const uint8_t *__restrict__ fate, const uint32_t *__restrict__ 
 // ---- P4: backward walk of the tile; every surviving byte is stored at its final position
 __global__ void __launch_bounds__(ACT_NT)
 ka_write(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles, const int32_t *__restrict__ h0,
-         const uint32_t *__restrict__ vec, const uint32_t *__restrict__ wlen, uint8_t *__restrict__ out) {
-  __shared__ uint32_t e[ACT_NSLOT * ACT_NT];
+         uint32_t nslots, const uint32_t *__restrict__ vec, const uint32_t *__restrict__ wlen,
+         uint8_t *__restrict__ out) {
+  uint32_t *e = act_sm;                                          // dynamic shared memory: nslots * ACT_NT * 4 bytes
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
@@ -508,11 +534,11 @@ ka_write(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntiles,
             if (b == 1u) {                            // undo push
               ACT_S(e, h) = eh; --h; eh = ACT_S(e, h);
             } else if (b & 1u) {                      // undo write r
-              const uint32_t N = ACT_NSLOT - 1u - ((b - 3u) >> 1);
+              const uint32_t N = nslots - 1u - ((b - 3u) >> 1);
               ACT_S(e, N) = eh;
               if (eh != ACT_NOPOS) eh -= wlen[(c + (size_t)k) >> 1];
             } else {                                  // undo pop r
-              const uint32_t N = ACT_NSLOT - 1u - ((b - 2u) >> 1);
+              const uint32_t N = nslots - 1u - ((b - 2u) >> 1);
               ACT_S(e, h) = eh; ++h;
               eh = ACT_S(e, N);
               ACT_S(e, N) = ACT_NOPOS;

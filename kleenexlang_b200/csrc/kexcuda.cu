@@ -1775,11 +1775,14 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
   CK(cudaStreamSynchronize(st));
   if (h.err & 5u) return KEX_ERR_ARG;                      // not an action stream
   if (h.err & 2u) return KEX_ERR_UNSUPPORTED;              // builders nested deeper than the slots allow
-  ka_fwd_summary<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, h0, fate, add);
+  // slots in use: builders 0..hmax and the registers (checked above to fit the 32 lanes of the scan kernels)
+  const uint32_t nslots = (uint32_t)h.hmax + 1u + ph.act_nregs;
+  const size_t cols = (size_t)nslots * ACT_NT;
+  ka_fwd_summary<<<tb, ACT_NT, cols * 8, st>>>(d_in, n, tile, ntiles, h0, nslots, fate, add);
   ka_group_compose<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gfate, gadd);
   ka_group_scan<<<1, 32, 0, st>>>(gfate, gadd, ngroups, gvec);
   ka_tile_vectors<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gvec, vec);
-  ka_fwd_exact<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, h0, vec, wlen, fate, add, ctl);
+  ka_fwd_exact<<<tb, ACT_NT, cols * 12, st>>>(d_in, n, tile, ntiles, h0, nslots, vec, wlen, fate, add, ctl);
   p->launches += 5;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1790,7 +1793,7 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
   ka_group_bcompose<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gfate, gadd);
   ka_group_bscan<<<1, 32, 0, st>>>(gfate, gadd, ngroups, ctl, gvec);
   ka_tile_bvectors<<<gb, 128, 0, st>>>(fate, add, ntiles, ngroups, gvec, vec);
-  ka_write<<<tb, ACT_NT, 0, st>>>(d_in, n, tile, ntiles, h0, vec, wlen, d_out);
+  ka_write<<<tb, ACT_NT, cols * 4, st>>>(d_in, n, tile, ntiles, h0, nslots, vec, wlen, d_out);
   p->launches += 4;
   CK(cudaGetLastError());
   return KEX_OK;
