@@ -119,15 +119,32 @@ ka_heights(const uint8_t *__restrict__ in, size_t n, uint32_t tile, size_t ntile
   bool bad = false;
   if (t < ntiles) {
     const size_t lo = t * tile, hi = (lo + tile < n) ? lo + tile : n;
-#define A_BYTE(i, v)
-#define A_PUSH(i) { ++h; u = h > u ? h : u; }
-#define A_POP(i, r) { --h; l = h < l ? h : l; bad |= (r) >= nregs; }
-#define A_WRITE(i, r) { bad |= (r) >= nregs; }
-    ACT_FWD_TOKENS(in, lo, hi, A_BYTE, A_PUSH, A_POP, A_WRITE)
-#undef A_BYTE
-#undef A_PUSH
-#undef A_POP
-#undef A_WRITE
+    // Branch-free over the four bytes of a word (this pass only counts, so the lanes of a warp need not
+    // diverge on the token kinds): E = bytes equal to ESC, O = bytes that follow an ESC = operands.
+    uint32_t pe = (lo > 0 && in[lo - 1] == ACT_ESC) ? 0x80u : 0u;
+#pragma unroll 1
+    for (size_t c = lo; c < hi; c += 4) {
+      const uint32_t cnt = (hi - c < 4) ? (uint32_t)(hi - c) : 4u;
+      const uint32_t w = act_ld4(in, c, cnt);
+      const uint32_t x = ~w;                                     // a byte of x is zero iff the byte of w is 0xFF
+      const uint32_t E = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+      const uint32_t O = (E << 8) | pe;
+      bad |= (E & O) != 0u;                                      // an operand is never ESC in an action stream
+      pe = E >> 24;                                              // 0x80 iff the word's last byte is an ESC
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t b = (w >> (8 * k)) & 0xFFu;
+        const int32_t o = (int32_t)((O >> (8 * k + 7)) & 1u);
+        const int32_t push = o & (int32_t)(b == 1u);
+        const int32_t reg_op = o & (int32_t)(b >= 2u);           // pop (even) or write (odd)
+        const int32_t pop = reg_op & (int32_t)((b & 1u) == 0u);
+        h += push;
+        u = h > u ? h : u;
+        h -= pop;
+        l = h < l ? h : l;
+        bad |= (reg_op != 0) && (((b - 2u) >> 1) >= nregs);
+      }
+    }
     delta[t] = h; mn[t] = l; mx[t] = u;
     if (bad) atomicOr(&ctl->err, 4u);
   }
