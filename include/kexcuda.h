@@ -61,6 +61,9 @@ typedef struct {
   uint32_t max_out_per_byte; /* worst-case output bytes per input byte, phase 0  */
   uint32_t chunk_bytes;    /* bytes one device chunk covers                      */
   uint32_t monoid_kernels; /* 1: phase 0 runs on the monoid kernels, 0: generic   */
+  uint32_t emit_kernel;    /* emit kernel family the next run of the phase uses: 4 = G-mode (kex_v4.cuh),
+                              3 = k3_emit, 2 = CTA-tile monoid kernels, 1 = generic                     */
+  uint32_t exact_tiles;    /* G-mode kernel, last run: tiles it had to evaluate exactly                 */
 } kex_info_t;
 
 /* Replaces the emit+cc step of compileProgram (C.hs:529-568) and `init()`

@@ -37,6 +37,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -631,6 +632,7 @@ __global__ void k_publish(const uint8_t *__restrict__ src, volatile uint8_t *dst
 
 #include "kex_fast.cuh"
 #include "kex_v3.cuh"
+#include "kex_v4.cuh"
 #include "kex_act.cuh"
 
 // =================================================================== host
@@ -660,6 +662,14 @@ struct PhaseHost {
   size_t smem_fwd3 = 0, smem_seams3 = 0;
   uint32_t v3_stage = 3072;           // per-warp staging window; follows the observed out/in ratio
   uint32_t v3_reccap = V3_RECCAP;     // template records per tile kept in shared memory; follows the observed maximum
+  // G-mode emit kernel (kex_v4.cuh); absent / switched off -> k3_emit
+  V4Dev v4;
+  void *d_v4 = nullptr;               // gtab, G, tpl, apply8
+  std::vector<uint32_t> h_trans2, h_BE, g_static_tab;   // host copies for learn_gmode
+  std::vector<uint8_t> g_static;      // [Q+1] the blob's static choice of G
+  bool v4_learned = false, v4_off = false;
+  uint32_t v4_relearns = 0, v4_last_exact = 0;
+  uint32_t v4_stage = 3072, v4_reccap = V4_RECCAP;
   // action-interpreter phase (kex_act.cuh): no SST tables at all
   bool act = false;
   uint32_t act_nregs = 0;
@@ -899,6 +909,166 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
   return KEX_OK;
 }
 
+
+// ---- G-mode tables (kex_v4.cuh).
+// gtab for a choice of G: observed (state, live set) pairs first, most frequent
+// first, each closed under the backward image (the live set of a predecessor
+// follows from its successor's), then the blob's static choice for the states
+// still open.  Same construction as fasttab.py build_gmode.
+static void build_gtab(const PhaseHost &ph, const std::vector<std::pair<uint32_t, uint32_t>> &observed,
+                       std::vector<uint8_t> &G, std::vector<uint32_t> &gtab) {
+  const uint32_t Q = ph.dev.Q, Q1 = Q + 1, C = ph.dev.C, A = ph.dev.A, NL = ph.fdev.NL;
+  const std::vector<uint32_t> &tr = ph.h_trans2, &BE = ph.h_BE;
+  auto lam_before = [&](uint32_t l, uint32_t a) { return ((BE[l * A + a] & 0xFFFCu) / 4u) / A; };
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> preds(Q1);
+  for (uint32_t q = 0; q < Q; ++q)
+    for (uint32_t c = 0; c < C; ++c) {
+      const uint32_t e = tr[q * C + c], q2 = e & 0xFFFFu;
+      if (q2 != Q) preds[q2].push_back({q, (e >> 16) & 0xFFu});
+    }
+  G.assign(Q1, 0xFF);
+  std::vector<uint32_t> work;
+  auto close = [&](uint32_t q0) {
+    work.assign(1, q0);
+    while (!work.empty()) {
+      const uint32_t q2 = work.back();
+      work.pop_back();
+      for (auto &pa : preds[q2])
+        if (G[pa.first] == 0xFF) {
+          G[pa.first] = (uint8_t)lam_before(G[q2], pa.second);
+          work.push_back(pa.first);
+        }
+    }
+  };
+  for (auto &o : observed)
+    if (o.first < Q && o.second < NL && G[o.first] == 0xFF) { G[o.first] = (uint8_t)o.second; close(o.first); }
+  for (uint32_t q = 0; q < Q; ++q)
+    if (G[q] == 0xFF && ph.g_static[q] != 0xFF) { G[q] = ph.g_static[q]; close(q); }
+  gtab.assign((size_t)Q1 * C, Q);
+  for (uint32_t q = 0; q < Q; ++q) {
+    if (G[q] == 0xFF) continue;
+    for (uint32_t c = 0; c < C; ++c) {
+      const uint32_t e = tr[q * C + c], q2 = e & 0xFFFFu, a = (e >> 16) & 0xFFu;
+      if (q2 == Q || G[q2] == 0xFF || lam_before(G[q2], a) != G[q]) continue;
+      const uint32_t be = BE[(uint32_t)G[q2] * A + a], typ = be & 3u;
+      uint32_t ln = (be >> 16) & 0xFFu, flags = 0;
+      if (typ == 0u) ln = 0;
+      else if (typ & 1u) { ln = 1; flags = V4_GB_C; }
+      else flags = V4_GB_T | (be >> 24);
+      gtab[q * C + c] = q2 | (ln << 16) | (flags << 24);
+    }
+  }
+}
+
+static int upload_gtab(kex_program *p, PhaseHost &ph, const std::vector<uint8_t> &G, const std::vector<uint32_t> &gtab,
+                       cudaStream_t st) {
+  CK(cudaMemcpyAsync((void *)ph.v4.gtab, gtab.data(), gtab.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync((void *)ph.v4.G, G.data(), G.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));          // the vectors are the caller's
+  return KEX_OK;
+}
+
+// The blob's G-mode sections (fasttab.py serialize_fast, header words 23..26).
+static int load_v4(kex_program *p, PhaseHost &ph, const uint8_t *f, uint32_t fl, const uint16_t *applyF,
+                   const uint32_t *trans2, const uint32_t *BE, const uint32_t *tplinfo, uint32_t NM, uint32_t NT) {
+  V4Dev &v = ph.v4;
+  memset(&v, 0, sizeof(v));
+  if (!ph.v3.ok || getenv("KEX_NO_V4") || rd32(f, 92) != 1u) return KEX_OK;
+  const FastDev &F = ph.fdev;
+  const uint32_t Q1 = ph.dev.Q + 1, C = ph.dev.C, A = ph.dev.A, NL = F.NL;
+  const uint32_t oG = rd32(f, 96), oT = rd32(f, 100), min_tpl = rd32(f, 104);
+  if ((size_t)oG + Q1 > fl || (size_t)oT + 4ull * Q1 * C > fl) return KEX_ERR_BAD_BLOB;
+  if (Q1 > 255 || NT > V4_MAX_TPL) return KEX_OK;
+  const uint32_t *gt = (const uint32_t *)(f + oT);
+  for (uint32_t i = 0; i < Q1 * C; ++i) {
+    const uint32_t e = gt[i], fl8 = e >> 24;
+    if ((e & 0xFFFFu) >= Q1 || ((fl8 & V4_GB_T) && (fl8 & 0x3Fu) >= NT) || ((fl8 & V4_GB_T) && (fl8 & V4_GB_C))) return KEX_ERR_BAD_BLOB;
+  }
+  for (uint32_t q = 0; q < Q1; ++q)
+    if (f[oG + q] != 0xFF && f[oG + q] >= NL) return KEX_ERR_BAD_BLOB;
+  // shared-memory layout: the replicated transition table must be addressable with 16 bits
+  const size_t tbytes = (size_t)Q1 * (C + 1) * 128;
+  if (tbytes + 2048 > 65536) return KEX_OK;
+  uint32_t sp = 0;
+  v.o_trans = sp; sp += (uint32_t)tbytes;
+  v.o_cls = sp; sp += 256;
+  v.apply_smem = ((size_t)NM * Q1 <= 64 * 1024) ? 1u : 0u;
+  v.o_apply = sp; if (v.apply_smem) sp += (NM * Q1 + 15u) & ~15u;
+  v.o_tpl = sp; sp += V4_MAX_TPL * 4u;
+  v.pool_stride = (F.pool_len + 4u + 12u + 3u) & ~3u;
+  v.o_pool = sp; sp += 4u * v.pool_stride;
+  sp = (sp + 15u) & ~15u;
+  v.o_slots = sp; sp += 256u + 512u;
+  sp = (sp + 127u) & ~127u;
+  v.o_warp = sp;
+  if (sp + 8u * (2048u + 128u + V4_RECCAP * 8u) > (uint32_t)V3_SMEM_MAX) return KEX_OK;
+  v.rmw = (min_tpl >= 3u || NT == 0u) ? 1u : 0u;
+  ph.h_trans2.assign(trans2, trans2 + (size_t)Q1 * C);
+  ph.h_BE.assign(BE, BE + (size_t)NL * A);
+  ph.g_static.assign(f + oG, f + oG + Q1);
+  ph.g_static_tab.assign(gt, gt + (size_t)Q1 * C);
+  std::vector<uint32_t> tpl(V4_MAX_TPL, 0);
+  for (uint32_t t = 0; t < NT; ++t) {
+    const uint32_t hm = tplinfo[2 * t + 1];
+    uint32_t hole = 0;
+    while (hm >> hole) ++hole;                              // hole offset + 1 (load_v3 has checked: at most one)
+    tpl[t] = (tplinfo[2 * t] & 0xFFFFu) | (tplinfo[2 * t] & 0xFF0000u) | (hole << 24);
+  }
+  std::vector<uint8_t> ap8((size_t)NM * Q1);
+  for (size_t i = 0; i < ap8.size(); ++i) ap8[i] = (uint8_t)applyF[i];
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_gt = 0, o_g = al(o_gt + 4ull * Q1 * C), o_tp = al(o_g + Q1), o_ap = al(o_tp + 4ull * V4_MAX_TPL),
+               tot = al(o_ap + ap8.size());
+  std::vector<uint8_t> img(tot, 0);
+  memcpy(img.data() + o_gt, gt, 4ull * Q1 * C);
+  memcpy(img.data() + o_g, f + oG, Q1);
+  memcpy(img.data() + o_tp, tpl.data(), 4ull * V4_MAX_TPL);
+  memcpy(img.data() + o_ap, ap8.data(), ap8.size());
+  CK(cudaMalloc(&ph.d_v4, tot));
+  CK(cudaMemcpy(ph.d_v4, img.data(), tot, cudaMemcpyHostToDevice));
+  const uint8_t *d = (const uint8_t *)ph.d_v4;
+  v.gtab = (const uint32_t *)(d + o_gt);
+  v.G = d + o_g;
+  v.tpl = (const uint32_t *)(d + o_tp);
+  v.apply8 = d + o_ap;
+  v.ok = 1;
+  ph.v4_learned = (NL == 1);                                // nothing to learn without registers
+  if (getenv("KEX_DEBUG"))
+    fprintf(stderr, "kexcuda: v4 (G-mode) emit kernel: tables %u B, element table %s, template edges %s\n", v.o_warp,
+            v.apply_smem ? "in shared memory" : "in global memory", v.rmw ? "merged" : "byte stores");
+  return KEX_OK;
+}
+
+// Learn G from the exact live sets at the chunk boundaries of the shard that is
+// about to be emitted (its state chain and live sets are on the device).
+static int learn_gmode(kex_program *p, PhaseHost &ph, size_t ntiles, cudaStream_t st) {
+  const size_t nchunks = (ntiles + V3_TPC - 1) / V3_TPC;
+  size_t N = nchunks > 1 ? nchunks - 1 : 0;               // boundaries c = 1..N: state starts[c], live set lams[0][4c-1]
+  if (N > 4096) N = 4096;
+  if (N < 2) return KEX_OK;                               // too little to learn from; the static table stays
+  std::vector<uint16_t> hs(N + 1);
+  std::vector<uint8_t> hl(4 * N);
+  CK(cudaMemcpyAsync(hs.data(), p->c->starts[0].p, (N + 1) * 2, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hl.data(), p->c->lams[0].p, 4 * N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::unordered_map<uint32_t, uint32_t> cnt;
+  for (size_t c = 1; c <= N; ++c) cnt[(uint32_t)hs[c] << 8 | hl[4 * c - 1]]++;
+  std::vector<std::pair<uint32_t, uint32_t>> order(cnt.begin(), cnt.end());
+  std::sort(order.begin(), order.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) {
+    return a.second != b.second ? a.second > b.second : a.first < b.first;
+  });
+  std::vector<std::pair<uint32_t, uint32_t>> obs;
+  for (auto &o : order) obs.push_back({o.first >> 8, o.first & 0xFFu});
+  std::vector<uint8_t> G;
+  std::vector<uint32_t> gtab;
+  build_gtab(ph, obs, G, gtab);
+  int rc = upload_gtab(p, ph, G, gtab, st);
+  if (rc) return rc;
+  ph.v4_learned = true;
+  if (getenv("KEX_DEBUG")) fprintf(stderr, "kexcuda: v4: G learnt from %zu chunk boundaries (%zu distinct pairs)\n", N, order.size());
+  return KEX_OK;
+}
+
 // Fast section (fasttab.py): monoid tables.  Malformed -> KEX_ERR_BAD_BLOB;
 // tables too large for shared memory -> the phase stays on the generic kernels.
 static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
@@ -965,7 +1135,9 @@ static int load_fast(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph
   d.pool = db + off[10];
   ph.smem_ef_tables = tables;
   ph.fast = true;
-  return load_v3(p, ph, mulF, applyF, BE, tplinfo, f + off[10], NM);
+  int rc = load_v3(p, ph, mulF, applyF, BE, tplinfo, f + off[10], NM);
+  if (rc) return rc;
+  return load_v4(p, ph, f, fl, applyF, trans2, BE, tplinfo, NM, NT);
 }
 
 static int load_phase(kex_program *p, const uint8_t *b, size_t len, PhaseHost &ph) {
@@ -1101,6 +1273,8 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
 #define V3_ATTR(L, R, T) cudaFuncSetAttribute(k3_emit<L, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
   V3_EACH(V3_ATTR)
 #undef V3_ATTR
+  cudaFuncSetAttribute(k4_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  cudaFuncSetAttribute(k4_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
   for (Ctx &c : p->cx) {
     if (cudaMallocHost((void **)&c.ctl_host, sizeof(FastCtl)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
@@ -1121,7 +1295,7 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
 extern "C" void kex_free(kex_program *p) {
   if (!p) return;
   cudaSetDevice(p->device);
-  for (auto &ph : p->phases) { cudaFree(ph.d_blob); cudaFree(ph.d_extra); cudaFree(ph.d_v3); }
+  for (auto &ph : p->phases) { cudaFree(ph.d_blob); cudaFree(ph.d_extra); cudaFree(ph.d_v3); cudaFree(ph.d_v4); }
   for (Ctx &c : p->cx) {
     for (int i = 0; i < 8; ++i) {
       cudaFree(c.maps[i].p); cudaFree(c.starts[i].p); cudaFree(c.fates[i].p); cudaFree(c.lives[i].p);
@@ -1155,6 +1329,9 @@ extern "C" int kex_info(const kex_program *p, uint32_t phase, kex_info_t *info) 
   info->max_out_per_byte = d.max_out; info->chunk_bytes = (uint32_t)p->phases[phase].tile();
   info->monoid_kernels = p->phases[phase].fast ? 1u : 0u;
   if (p->phases[phase].act) info->chunk_bytes = 1024u;
+  const PhaseHost &ph = p->phases[phase];
+  info->emit_kernel = (ph.v4.ok && !ph.v4_off) ? 4u : ph.v3.ok ? 3u : ph.fast ? 2u : 1u;
+  info->exact_tiles = ph.v4_last_exact;
   return KEX_OK;
 }
 
@@ -1533,6 +1710,74 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
   if ((rc = ensure(p, p->c->ctl, sizeof(FastCtl)))) return rc;
   CK(cudaMemsetAsync(p->c->desc.p, 0, ntiles * 8, st));
   CK(cudaMemsetAsync(p->c->ctl.p, 0, sizeof(FastCtl), st));
+  if (ph.v4.ok && !ph.v4_off) {
+    // G-mode emit kernel (kex_v4.cuh): same launch geometry as k3_emit below
+    const V4Dev &V = ph.v4;
+    if (!ph.v4_learned && (rc = learn_gmode(p, ph, ntiles, st))) return rc;
+    if (const char *e = getenv("KEX_V4_STAGE")) { const long x = atol(e); if (x >= 256) ph.v4_stage = (uint32_t)x & ~127u; }
+    if (const char *e = getenv("KEX_V4_RECCAP")) { const long x = atol(e); if (x >= 8) ph.v4_reccap = (uint32_t)x; }
+    const uint32_t force_exact = getenv("KEX_V4_EXACT") ? 1u : 0u;
+    const uint32_t warp_bytes = (ph.v4_stage + 128u + ph.v4_reccap * 8u + 127u) & ~127u;
+    uint32_t nwork = (uint32_t)(((size_t)V3_SMEM_MAX - V.o_warp) / warp_bytes);
+    if (nwork > 31u) nwork = 31u;
+    if (const char *e = getenv("KEX_V3_WORKERS")) { const uint32_t x = (uint32_t)atoi(e); if (x >= 1 && x < nwork) nwork = x; }
+    if (nwork < 1u) return KEX_ERR_UNSUPPORTED;
+    const size_t smem4 = (size_t)V.o_warp + (size_t)nwork * warp_bytes;
+    const uint32_t nwarp = nwork + 1u;
+    const bool regs = NL > 1;
+    int occ = 0;
+    if (regs) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_emit<true>, (int)(nwarp * 32u), smem4));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_emit<false>, (int)(nwarp * 32u), smem4));
+    if (occ < 1) return KEX_ERR_UNSUPPORTED;
+    const size_t ngroups = (ntiles + nwork - 1) / nwork;
+    size_t ctas = ngroups;
+    if (ctas > (size_t)occ * (size_t)p->num_sms) ctas = (size_t)occ * (size_t)p->num_sms;
+    if (p->timing) CK(cudaEventRecord(p->ev[4], st));
+    if (regs)
+      k4_emit<true><<<(unsigned)ctas, nwarp * 32u, smem4, st>>>(
+          P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,
+          (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,
+          (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,
+          (unsigned long long)p->emit_out_off, ph.v4_stage, warp_bytes, ph.v4_reccap, force_exact);
+    else
+      k4_emit<false><<<(unsigned)ctas, nwarp * 32u, smem4, st>>>(
+          P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,
+          (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,
+          (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,
+          (unsigned long long)p->emit_out_off, ph.v4_stage, warp_bytes, ph.v4_reccap, force_exact);
+    p->launches++;
+    if (p->timing) CK(cudaEventRecord(p->ev[5], st));
+    CK(cudaGetLastError());
+    if ((rc = fetch_sync(p, p->c->ctl_host, p->c->ctl.p, sizeof(FastCtl), st))) return rc;
+    if (p->c->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
+    const size_t total = (size_t)p->c->ctl_host->total_out;
+    *out_len = total;
+    if (p->c->ctl_host->overflow || total + p->emit_out_off > out_cap) return KEX_ERR_OUT_CAP;
+    // tiles that were evaluated exactly: when many, G no longer fits the data -- learn it again from
+    // the next run's live sets; a program whose live sets are not state-determined (thousand_sep:
+    // they follow the digit count) goes back to k3_emit for good
+    const size_t slow = p->c->ctl_host->ticket;
+    ph.v4_last_exact = (uint32_t)slow;
+    if (!force_exact && regs && ntiles >= 64 && slow * 8 > ntiles) {
+      if (++ph.v4_relearns > 2) ph.v4_off = true; else ph.v4_learned = false;
+      if (getenv("KEX_DEBUG")) fprintf(stderr, "kexcuda: v4: %zu of %zu tiles evaluated exactly -> %s\n", slow, ntiles,
+                                       ph.v4_off ? "back to k3_emit" : "G will be learnt again");
+    }
+    if (getenv("KEX_V4_STAGE") || getenv("KEX_V4_RECCAP")) return KEX_OK;
+    // size the staging windows and record slots for the next run from what this one saw
+    const double per_tile = (double)total / (double)ntiles;
+    uint32_t want = (uint32_t)(per_tile * 1.25) + 256;
+    want = (want + 255u) & ~255u;
+    if (want < 2048u) want = 2048u;
+    uint32_t wrec = (p->c->ctl_host->pad + p->c->ctl_host->pad / 4u + 32u + 63u) & ~63u;
+    if (wrec < V4_RECCAP) wrec = V4_RECCAP;
+    if (wrec > 1024u) wrec = 1024u;
+    if (wrec > ph.v4_reccap || wrec + 128u < ph.v4_reccap) ph.v4_reccap = wrec;
+    const uint32_t stage_max = (uint32_t)(((V3_SMEM_MAX - V.o_warp) / 8u - 128u - ph.v4_reccap * 8u) & ~255u);   // keep >= 8 warps
+    if (want > stage_max) want = stage_max;
+    if (want > ph.v4_stage || want + 1024u < ph.v4_stage) ph.v4_stage = want;
+    return KEX_OK;
+  }
   if (ph.v3.ok) {
     // one CTA per SM: up to 31 worker warps + 1 scan warp (as many workers as the
     // staging windows leave room for); every CTA must be resident because groups

@@ -26,7 +26,8 @@ class KexError(RuntimeError):
 
 class KexInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
-        "nphases", "nstates", "nclasses", "nregs", "nactions", "max_out_per_byte", "chunk_bytes", "monoid_kernels")]
+        "nphases", "nstates", "nclasses", "nregs", "nactions", "max_out_per_byte", "chunk_bytes", "monoid_kernels",
+        "emit_kernel", "exact_tiles")]
 
 
 EXPORTS = ["kex_load", "kex_free", "kex_info", "kex_run_device", "kex_run_host", "kex_shard_summarize",

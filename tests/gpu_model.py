@@ -241,3 +241,73 @@ def run_fast_model(t, f, data: bytes, chunk: int = 64, sub: int = 8):
         return True, bytes(out), n
     keep = len(out) // 16384 * 16384
     return False, bytes(out[:keep]), n_eff
+
+
+def run_gmode_model(t, f, gm, data: bytes, tile: int = 64):
+    """Model of the G-mode emit kernel (csrc/kex_v4.cuh) on an accepted input:
+    a tile whose exact end live set equals G[end state] and whose G-mode walk
+    never reaches the FAIL row is emitted from the G-mode table alone; any
+    other tile from the exact live sets.  Returns (output, tiles emitted in
+    G-mode, tiles)."""
+    from kleenexlang_b200.fasttab import E_SYM, E_TPL, GB_T, GB_C
+    G, gtab, _ = gm
+    Q, C, A = t.Q, t.C, t.A
+    n = len(data)
+    states, acts = [t.init], []
+    for b in data:
+        e = f.trans2[states[-1] * C + t.cls[b]]
+        assert (e & 0xFFFF) != Q, "model is for accepted inputs"
+        states.append(e & 0xFFFF)
+        acts.append((e >> 16) & 0xFF)
+    assert t.final[states[-1]] >= 0
+    lam = [0] * (n + 1)
+    lam[n] = f.lam_final[states[-1]]
+    for i in range(n - 1, -1, -1):
+        lam[i] = ((f.BE[lam[i + 1] * A + acts[i]] & 0xFFFC) // 4) // A
+
+    def template(x, b):
+        info, hmask = f.tplinfo[2 * x], f.tplinfo[2 * x + 1]
+        off, tl = info & 0xFFFF, (info >> 16) & 0xFF
+        seg = bytearray(f.pool[off:off + tl])
+        for h in range(min(tl, 32)):
+            if (hmask >> h) & 1:
+                seg[h] = b
+        return seg
+
+    out = bytearray()
+    ntiles = (n + tile - 1) // tile
+    gtiles = 0
+    for k in range(ntiles):
+        lo, hi = k * tile, min(n, (k + 1) * tile)
+        ok = hi - lo == tile and G[states[hi]] == lam[hi]
+        seg = bytearray()
+        if ok:
+            q = states[lo]
+            for i in range(lo, hi):
+                e = gtab[q * C + t.cls[data[i]]]
+                q = e & 0xFFFF
+                if q == Q:
+                    ok = False
+                    break
+                ln, fl = (e >> 16) & 0xFF, e >> 24
+                if fl & GB_T:
+                    s2 = template(fl & 0x3F, data[i])
+                    assert len(s2) == ln
+                    seg += s2
+                elif fl & GB_C:
+                    seg.append(data[i])
+        if ok:
+            gtiles += 1
+        exact = bytearray()
+        for i in range(lo, hi):
+            e = f.BE[lam[i + 1] * A + acts[i]]
+            if (e & 3) == E_SYM:
+                exact.append(data[i])
+            elif (e & 3) == E_TPL:
+                exact += template(e >> 24, data[i])
+        if ok:
+            assert seg == exact, "G-mode tile differs from the exact evaluation"
+        out += exact
+    for tgt, kind, ln, off in t.pieces[t.final[states[-1]]]:
+        out += t.consts[off:off + ln]
+    return bytes(out), gtiles, ntiles

@@ -266,6 +266,66 @@ def test_v3_paths_forced(name, knob, monkeypatch):
     _check(prog, ssts, d[:1000000] + b"\x01" + d[1000001:])
 
 
+V4_PROGS = ["csv2json", "iso_datetime_to_json", "fastq2fasta"]
+
+
+@pytest.mark.parametrize("name", PROGS)
+@pytest.mark.parametrize("knob", [{}, {"KEX_V4_EXACT": "1"}, {"KEX_V4_STAGE": "256", "KEX_V4_RECCAP": "8"}, {"KEX_NO_V4": "1"},
+                                  {"KEX_V3_WORKERS": "3"}])
+def test_v4_paths_forced(name, knob, monkeypatch):
+    """The G-mode emit kernel (kex_v4.cuh) and its rarely taken paths, forced:
+    every tile evaluated exactly from the tables in global memory
+    (KEX_V4_EXACT), tiles that do not fit the staging window / record slots
+    (byte stores to global), k3_emit instead (KEX_NO_V4), few worker warps per
+    CTA (many groups per CTA: the chained scan and the deferred stage-out).
+    Inputs long enough for G to be learnt from the run itself (>= 2 chunk
+    boundaries), twice (the second run uses the learnt table and the window
+    sized from the first), truncated, and rejecting."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    for k, v in knob.items():
+        monkeypatch.setenv(k, v)
+    prog = CompiledProgram(compile_kex(program_source(name)))          # KEX_NO_V4 is read at load time
+    ssts = build_ssts(program_source(name))
+    assert prog.info()["chunk_bytes"] == 1024
+    d = workloads.GENERATORS[name](3 << 20, seed=62).tobytes()
+    _check(prog, ssts, d)
+    _check(prog, ssts, d)
+    _check(prog, ssts, d[:700001])
+    _check(prog, ssts, d[:5000])
+    _check(prog, ssts, d[:1000000] + b"\x01" + d[1000001:])
+    prog.close()
+
+
+@pytest.mark.parametrize("name", V4_PROGS)
+def test_v4_gmode_taken(name, monkeypatch, capfd):
+    """csv2json, iso_datetime and fastq2fasta have state-determined live sets:
+    once G is learnt from the run, (nearly) every tile goes through the G-mode
+    passes -- the library reports how many tiles it evaluated exactly."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    prog = CompiledProgram(compile_kex(program_source(name)))
+    ssts = build_ssts(program_source(name))
+    d = workloads.GENERATORS[name](4 << 20, seed=63).tobytes()
+    _check(prog, ssts, d)
+    inf = prog.info()
+    assert inf["emit_kernel"] == 4
+    assert inf["exact_tiles"] <= 4, inf
+    prog.close()
+
+
+def test_v4_not_state_determined():
+    """thousand_sep: the live sets follow the digit count, not the state; after
+    a few runs with most tiles evaluated exactly the phase goes back to k3_emit
+    (output identical all along)."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    prog = CompiledProgram(compile_kex(program_source("thousand_sep")))
+    ssts = build_ssts(program_source("thousand_sep"))
+    d = workloads.GENERATORS["thousand_sep"](2 << 20, seed=64).tobytes()
+    for _ in range(5):
+        _check(prog, ssts, d)
+    assert prog.info()["emit_kernel"] == 3
+    prog.close()
+
+
 @pytest.mark.parametrize("nolit", [False, True])
 def test_one_byte_literals(nolit, monkeypatch):
     """An action that replaces its input byte by a different one-byte literal:

@@ -111,3 +111,78 @@ def test_fast_section_in_blob():
     blob = compile_kex(program_source("apache_log"))
     off = struct.unpack_from("<I", blob, 16)[0]
     assert struct.unpack_from("<II", blob, off + 76) == (0, 0)
+
+
+# ---- G-mode tables (fasttab.build_gmode, csrc/kex_v4.cuh)
+from gpu_model import run_gmode_model
+
+
+def _observed_pairs(t, f, data, tile, upto):
+    """(state, live set) at the tile ends before `upto`, most frequent first --
+    what the host library reads back from the device before it builds the
+    G-mode table."""
+    import collections
+    Q, C, A = t.Q, t.C, t.A
+    states, acts = [t.init], []
+    for b in data:
+        e = f.trans2[states[-1] * C + t.cls[b]]
+        states.append(e & 0xFFFF)
+        acts.append((e >> 16) & 0xFF)
+    n = len(data)
+    lam = [0] * (n + 1)
+    lam[n] = f.lam_final[states[-1]]
+    for i in range(n - 1, -1, -1):
+        lam[i] = ((f.BE[lam[i + 1] * A + acts[i]] & 0xFFFC) // 4) // A
+    cnt = collections.Counter((states[i], lam[i]) for i in range(tile, upto, tile))
+    return [k for k, _ in cnt.most_common()]
+
+
+@pytest.mark.parametrize("prog,expect_all", [("csv2json", True), ("iso_datetime_to_json", True), ("fastq2fasta", True),
+                                             ("thousand_sep", False), ("add-commas", False)])
+def test_gmode_model(prog, expect_all):
+    """A tile emitted from the G-mode table alone (end live set == G[end state],
+    FAIL row never reached) equals the exact evaluation -- asserted inside the
+    model for every such tile -- and the whole output equals the oracle's, with
+    the static table and with a table learnt from the first third of the input.
+    Programs whose live sets follow the state run (nearly) every tile in G-mode
+    once the table is learnt; thousand_sep's follow the digit count and do not."""
+    ssts = build_ssts(program_source(prog), 3)
+    t = build_phase(ssts[0])
+    f = fasttab.build_fast(t)
+    data = workloads.GENERATORS[prog](60000, seed=8).tobytes()
+    exp = oracle_run(ssts, data)
+    assert exp[0] == 0
+    for tile in (32, 1024):
+        static = fasttab.build_gmode(t, f)
+        assert static is not None
+        out, _, _ = run_gmode_model(t, f, static, data, tile)
+        assert out == exp[1]
+        learnt = fasttab.build_gmode(t, f, _observed_pairs(t, f, data, tile, 20000))
+        out, g, nt = run_gmode_model(t, f, learnt, data, tile)
+        assert out == exp[1]
+        if expect_all:
+            assert g >= nt - 8, (prog, tile, g, nt)          # all but the tiles of the last record
+        else:
+            assert g < nt // 2
+
+
+def test_gmode_sections_in_blob():
+    import struct
+    for prog in ("csv2json", "fastq2fasta"):
+        blob = compile_kex(program_source(prog))
+        off = struct.unpack_from("<I", blob, 16)[0]
+        fast_off = struct.unpack_from("<I", blob, off + 76)[0]
+        hdr = struct.unpack_from("<32I", blob, off + fast_off)
+        t = build_phase(build_ssts(program_source(prog))[0])
+        f = fasttab.build_fast(t)
+        G, gtab, min_tpl = fasttab.build_gmode(t, f)
+        assert hdr[23] == 1 and hdr[26] == min_tpl
+        base = off + fast_off
+        assert list(blob[base + hdr[24]:base + hdr[24] + t.Q + 1]) == G
+        assert list(struct.unpack_from("<%dI" % len(gtab), blob, base + hdr[25])) == gtab
+        # row Q (FAIL) absorbs; every entry is a copy, a template of a valid id, or nothing
+        assert all(e == t.Q for e in gtab[t.Q * t.C:])
+        for e in gtab:
+            fl = e >> 24
+            assert (e & 0xFFFF) <= t.Q and not (fl & 0x80 and fl & 0x40)
+            assert not (fl & 0x80) or (fl & 0x3F) < f.NT
