@@ -9,8 +9,9 @@ LIB = os.path.join(HERE, "libkexcuda.so")
 
 
 def build(force=False, verbose=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(
-            os.path.getmtime(SRC), os.path.getmtime(os.path.join(HERE, "..", "include", "kexcuda.h"))):
+    deps = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
+    deps.append(os.path.join(HERE, "..", "include", "kexcuda.h"))
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB, SRC]

@@ -31,7 +31,9 @@
 //   Any other tile (the last rows of the input, tiles that would overflow the
 //   window) is evaluated exactly by v4_slow_count / v4_slow_write from the
 //   tables in global memory -- rare, so slow is fine; KEX_V4_EXACT=1 forces it
-//   for every tile (tests).
+//   for every tile (tests).  KEX_V4_KNOCK (bits 2/4/8/16 of force_exact: no write
+//   pass / no templates / no stage-out / no look-back) is for timing experiments
+//   only: the output is wrong.
 #pragma once
 
 #define V4_RECCAP 192u
@@ -51,7 +53,11 @@ struct V4Dev {
   const uint8_t *apply8;    // [NM*(Q+1)] applyF as bytes
 };
 
+#ifdef KEX_EXP_NOSWZ
+__device__ __forceinline__ uint32_t swz4(uint32_t a) { return a; }
+#else
 __device__ __forceinline__ uint32_t swz4(uint32_t a) { return a ^ ((a >> 3) & 0x70u); }
+#endif
 __device__ __forceinline__ uint32_t mad_hi_u32(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r;
   asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
@@ -88,7 +94,11 @@ __device__ __forceinline__ void v4_write_half(const uint32_t (&w)[8], const uint
     const uint32_t wreg = w[4 * H + (j >> 2)];
     const int k = j & 3;
     const bool hi = (j & 1) != 0;
+#ifdef KEX_EXP_BANKPRIV
+    const uint32_t addr = (a & 3u) + ((threadIdx.x & 31u) << 2) + 0x8000u;      // timing only: one bank per lane
+#else
     const uint32_t addr = swz4(a);
+#endif
     const uint32_t b = k == 0 ? wreg : __umulhi(wreg, 1u << (32 - 8 * k));
     if (p & (hi ? 0x40000000u : 0x4000u)) sts_u8(addr, b);
     if (p & (hi ? 0x80000000u : 0x8000u)) {
@@ -338,6 +348,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       unsigned long long gex = 0;
       long long idx = (long long)grp - 1;
       bool ok = true;
+      if (force_exact & 16u) idx = -1;
       while (idx >= 0 && ok) {
         unsigned long long d[8];
 #pragma unroll
@@ -405,7 +416,8 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     uint32_t sA = Q, sB = Q;
     if (cnt_pos) {
       const uint32_t cs = chunk_start[tile / V3_TPC];
-      const uint32_t smp = *(const uint32_t *)(samples + (size_t)tile * V3_SPT + 2u * lane);
+      uint32_t smp = *(const uint32_t *)(samples + (size_t)tile * V3_SPT + 2u * lane);
+      if (cnt_pos <= 16u) smp &= 0xFFFFu;               // the second half lies past the input: its sample was never written
       const uint32_t bp = blockpre[(size_t)tile * (V3_TILE / V3_BLK) + (lane >> 2)];     // 4 lanes per 128-byte block
       if (V.apply_smem) {
         const uint32_t ap_abs = base + V.o_apply;
@@ -423,7 +435,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     // ---- forward walk over the G-mode table: emission halves of the entries, lengths, template counts
     uint32_t pr[16];
     uint32_t cntA = 0, cntB = 0, nrA = 0, nrB = 0;
-    bool gmode = full && !force_exact;
+    bool gmode = full && !(force_exact & 1u);
     if (gmode) {
       uint32_t EA = trans_abs + sA * row_bytes + slot4, EB = trans_abs + sB * row_bytes + slot4;
 #pragma unroll
@@ -457,6 +469,14 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       cntA = sl.cnt; cntB = 0; nrA = sl.nrec; nrB = 0;
       if (active) ++slow_tiles;
     }
+#ifdef KEX_EXP_PAD_ALU
+    {
+      uint32_t z = cntA;
+#pragma unroll
+      for (int i = 0; i < KEX_EXP_PAD_ALU; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z) : "r"(cntB), "r"(lane));
+      if (z == 0xDEADBEEFu) cntA += 1;
+    }
+#endif
     const uint32_t v = (cntA + cntB) | ((nrA + nrB) << 20);
     uint32_t xs = v;
 #pragma unroll
@@ -486,7 +506,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       const unsigned long long gb = bases[(par ^ 1u) * 32u + warp];
       if (gb + prev_total > (unsigned long long)out_cap) {
         if (lane == 0) atomicExch(&ctl->overflow, 1u);
-      } else {
+      } else if (!(force_exact & 8u)) {
         v4_stage_out(stage_abs, prev_total, gb, out, lane);
       }
       __syncwarp();
@@ -496,7 +516,8 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     const uint32_t rec_excl = (xs >> 20) - (nrA + nrB);
     max_recs = total_recs > max_recs ? total_recs : max_recs;
     if (total + 16u <= stage_bytes && total_recs <= reccap) {
-      if (gmode) {
+      if (gmode && (force_exact & 2u)) {
+      } else if (gmode) {
         const uint32_t aA = stage_abs + o_end - cntA - cntB, aB = aA + cntA;
         const uint32_t recpA = recs_abs + 8u * rec_excl, recpB = recpA + 8u * nrA;
         v4_write_half<0>(w, pr, aA, recpA);
@@ -507,7 +528,8 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       __syncwarp();
       // ---- templates: one lane per record.  Merging variant: even records, then odd ones (two
       // neighbours may share a word; records two apart never do when every template has >= 3 bytes)
-      if (V.rmw) {
+      if (force_exact & 4u) {
+      } else if (V.rmw) {
         for (uint32_t ph = 0; ph < 2u; ++ph) {
           for (uint32_t r = 2u * lane + ph; r < total_recs; r += 64u)
             v4_template_rmw(pool_abs, V.pool_stride, tpl_abs, lds_u32_v(recs_abs + 8u * r), lds_u32_v(recs_abs + 8u * r + 4u));

@@ -1716,7 +1716,8 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     if (!ph.v4_learned && (rc = learn_gmode(p, ph, ntiles, st))) return rc;
     if (const char *e = getenv("KEX_V4_STAGE")) { const long x = atol(e); if (x >= 256) ph.v4_stage = (uint32_t)x & ~127u; }
     if (const char *e = getenv("KEX_V4_RECCAP")) { const long x = atol(e); if (x >= 8) ph.v4_reccap = (uint32_t)x; }
-    const uint32_t force_exact = getenv("KEX_V4_EXACT") ? 1u : 0u;
+    uint32_t force_exact = getenv("KEX_V4_EXACT") ? 1u : 0u;
+    if (const char *e = getenv("KEX_V4_KNOCK")) force_exact |= (uint32_t)atoi(e) & ~1u;     // timing experiments only (wrong output)
     const uint32_t warp_bytes = (ph.v4_stage + 128u + ph.v4_reccap * 8u + 127u) & ~127u;
     uint32_t nwork = (uint32_t)(((size_t)V3_SMEM_MAX - V.o_warp) / warp_bytes);
     if (nwork > 31u) nwork = 31u;
@@ -1759,7 +1760,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     const size_t slow = p->c->ctl_host->ticket;
     ph.v4_last_exact = (uint32_t)slow;
     if (!force_exact && regs && ntiles >= 64 && slow * 8 > ntiles) {
-      if (++ph.v4_relearns > 2) ph.v4_off = true; else ph.v4_learned = false;
+      if (++ph.v4_relearns > 1) ph.v4_off = true; else ph.v4_learned = false;
       if (getenv("KEX_DEBUG")) fprintf(stderr, "kexcuda: v4: %zu of %zu tiles evaluated exactly -> %s\n", slow, ntiles,
                                        ph.v4_off ? "back to k3_emit" : "G will be learnt again");
     }

@@ -10,7 +10,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkexcuda.so")
+# KEX_LIB: an alternative build of the same library (kernel experiments: scripts/build_exp.py)
+LIB_PATH = os.environ.get("KEX_LIB") or os.path.join(HERE, "libkexcuda.so")
 
 KEX_OK, KEX_ERR_OUT_CAP = 0, -3
 ACCEPT, REJECT = 0, 1

@@ -19,4 +19,6 @@ for i in range(3):
     st, olen, _ = prog.run_device(d_in.data_ptr(), n, d_out.data_ptr(), d_out.numel())
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
 k = prog.kernel_ms()
-print("%s %.2f GiB: %.1f GiB/s in (fwd %.2f seams %.2f emit %.2f all %.2f ms)" % (name, n / 2**30, n / dt / 2**30, k[0], k[1], k[2], k[3]))
+inf = prog.info()
+print("%s %.2f GiB: %.1f GiB/s in (fwd %.2f seams %.2f emit %.2f all %.2f ms) emit_kernel %d exact_tiles %d" % (
+    name, n / 2**30, n / dt / 2**30, k[0], k[1], k[2], k[3], inf["emit_kernel"], inf["exact_tiles"]))
