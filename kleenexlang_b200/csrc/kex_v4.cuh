@@ -281,8 +281,11 @@ __device__ __noinline__ void v4_slow_write(const PhaseDev &P, const FastDev &F, 
 }
 
 // ------------------------------------------------------------------ k4_emit
+#ifndef KEX_V4_THREADS
+#define KEX_V4_THREADS 1024
+#endif
 template <bool REGS>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(KEX_V4_THREADS, 1)
 k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
         const uint16_t *__restrict__ samples, const uint16_t *__restrict__ blockpre,
         const uint16_t *__restrict__ chunk_start, const uint8_t *__restrict__ lam_end,

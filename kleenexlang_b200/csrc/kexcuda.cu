@@ -1976,7 +1976,16 @@ extern "C" int kex_shard_emit(kex_program *p, uint32_t live_end_mask, size_t n_e
                               size_t *out_len, void *stream) {
   if (!p || !out_len || n_eff > p->c->sh_n) return KEX_ERR_ARG;
   CK(cudaSetDevice(p->device));
-  return do_emit(p, live_end_mask, n_eff, d_out, out_cap, out_len, (cudaStream_t)stream);
+  const int rc = do_emit(p, live_end_mask, n_eff, d_out, out_cap, out_len, (cudaStream_t)stream);
+  if (rc == KEX_OK && p->timing && p->ev_ok && cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess) {
+    // kernel times of this shard's three steps (kex_last_kernel_ms): forward, seams, emit
+    if (cudaEventElapsedTime(&p->ms[0], p->ev[0], p->ev[1]) != cudaSuccess) p->ms[0] = 0.f;
+    if (cudaEventElapsedTime(&p->ms[1], p->ev[2], p->ev[3]) != cudaSuccess) p->ms[1] = 0.f;
+    if (!*out_len || cudaEventElapsedTime(&p->ms[2], p->ev[4], p->ev[5]) != cudaSuccess) p->ms[2] = 0.f;
+    p->ms[3] = 0.f;
+    cudaGetLastError();
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------ whole pipeline
