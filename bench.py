@@ -571,7 +571,7 @@ def main():
                                               "all_device_work": kms[3] if world == 1 else None},
                                 "note": "per GPU; kernel times are the max over ranks" if world > 1 else "1 GPU",
                                 "pipeline_frac": (total_n + total_reps * P) / world / (ms_per_step / 1000.0) / 1e9 / peak}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # a reported baseline, at N=1 only
             line["cpu_baseline"] = cpu_baseline(cfg["gen"])
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
