@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import load_vectors, vec_matches, program_source, sample, ROOT
+from conftest import load_vectors, vec_matches, program_source, sample, ROOT, GOLDEN
 from kleenexlang_b200 import workloads
 from kleenexlang_b200.frontend.driver import build_ssts
 from kleenexlang_b200.kexprog import compile_kex, UnsupportedProgram
@@ -52,6 +52,20 @@ def test_bundled_samples(name, fixture):
     st, out, _ = prog.run(d)
     est, eout, _ = oracle_run(ssts, d)
     assert (st, out) == (est, eout)
+
+
+def test_csv2json_pinned_output():
+    """The CUDA path against the committed csv2json output that was derived
+    from the reference's Ragel equivalent, not from the restated front end
+    (scripts/make_csv2json_pin.py), and against that restatement on 4 MiB."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from make_csv2json_pin import csv2json_rl
+    prog, _ = gpu_prog(program_source("csv2json"))
+    want = open(os.path.join(GOLDEN, "csv2json_sample.out"), "rb").read()
+    assert prog.run(sample("csv_sample.csv"))[:2] == (0, want)
+    big = workloads.gen_csv(4 << 20, seed=22).tobytes()
+    assert prog.run(big)[:2] == (0, csv2json_rl(big))
 
 
 PROGS = ["csv2json", "iso_datetime_to_json", "thousand_sep", "add-commas", "fastq2fasta"]

@@ -35,6 +35,26 @@ def test_oracle_cross_tool():
     assert out.decode().startswith(cross["csv2json"]["first_record"])
 
 
+def test_csv2json_pinned_by_independent_restatement():
+    """csv2json has no golden output in the reference; pin it by a restatement
+    of the reference's own Ragel equivalent (bench/ragel/src/csv2json.rl) that
+    shares nothing with the restated front end: the reference's 10-row sample
+    (committed output tests/golden/csv2json_sample.out, 1878 bytes) and 1 MiB of
+    the synthetic CSV the benchmark uses."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from make_csv2json_pin import csv2json_rl
+    ssts = build_ssts(program_source("csv2json"))
+    d = sample("csv_sample.csv")
+    want = open(os.path.join(GOLDEN, "csv2json_sample.out"), "rb").read()
+    assert len(want) == 1878 and csv2json_rl(d) == want
+    assert oracle_run(ssts, d)[:2] == (0, want)
+    if os.path.exists(os.path.join(REF, "csv2json")):
+        assert _ref("csv2json", d)[:2] == (0, want)
+    big = workloads.gen_csv(1 << 20, seed=21).tobytes()
+    assert oracle_run(ssts, big)[:2] == (0, csv2json_rl(big))
+
+
 def _ref(name, data):
     r = subprocess.run([os.path.join(REF, name)], input=data, capture_output=True)
     return r.returncode, r.stdout, r.stderr
