@@ -25,5 +25,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+KEXRUN = os.path.join(HERE, "kexrun")
+
+
+def build_kexrun(force=False):
+    """The native launcher (tools/kexrun.c): binds the C ABI from C with dlopen; `kexc compile --out`
+    installs a copy of it next to the program blob."""
+    src = os.path.join(HERE, "..", "tools", "kexrun.c")
+    if not force and os.path.exists(KEXRUN) and os.path.getmtime(KEXRUN) >= os.path.getmtime(src):
+        return KEXRUN
+    r = subprocess.run(["cc", "-O2", "-I", os.path.join(HERE, "..", "include"), src, "-ldl", "-o", KEXRUN],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("cc failed:\n" + r.stdout + r.stderr)
+    return KEXRUN
+
+
 if __name__ == "__main__":
+    print(build_kexrun(force=True))
     print(build(force=True, verbose="-v" in sys.argv))

@@ -222,6 +222,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long ef_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -485,9 +490,10 @@ k_emit_fast(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n_eff,
         const long long j = idx - lane;
         unsigned long long d = EF_FLAG_INC;
         if (j >= 0) {
+          const unsigned long long t0 = ef_globaltimer();           // give up only after 20 s of wall time
           uint32_t spins = 0;
           while (((d = ld_desc(desc + j)) >> 62) == 0) {
-            if (++spins > (1u << 22)) break;
+            if ((++spins & 1023u) == 0u && ef_globaltimer() - t0 > 20000000000ull) break;
             __nanosleep(20);
           }
         }

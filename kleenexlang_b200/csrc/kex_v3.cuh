@@ -638,11 +638,16 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
         for (int k = 0; k < 8; ++k) {
           if (!hit) {
             const long long j = idx - (long long)(lane + 32u * k);
-            uint32_t spins = 0;
-            while ((d[k] >> 62) == 0) {
-              if (++spins > (1u << 22)) break;
-              __nanosleep(20);
-              d[k] = ld_desc(desc + j);
+            if ((d[k] >> 62) == 0) {
+              // a predecessor that has not published yet: poll; give up only after 20 s of wall time
+              // (a descheduled predecessor on a time-sliced GPU must not fail a correct run)
+              const unsigned long long t0 = ef_globaltimer();
+              uint32_t spins = 0;
+              while ((d[k] >> 62) == 0) {
+                if ((++spins & 1023u) == 0u && ef_globaltimer() - t0 > 20000000000ull) break;
+                __nanosleep(20);
+                d[k] = ld_desc(desc + j);
+              }
             }
             if (__any_sync(0xFFFFFFFFu, (d[k] >> 62) == 0)) { ok = false; hit = true; }
             const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (d[k] >> 62) == 2);

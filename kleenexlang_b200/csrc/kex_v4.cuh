@@ -44,6 +44,7 @@
 struct V4Dev {
   uint32_t ok;
   uint32_t o_trans, o_cls, o_apply, o_tpl, o_pool, o_slots, o_warp;   // byte offsets in dynamic smem
+  uint32_t log;             // log2 of the transition table's entry stride (7: per-lane copies, 6: two lanes per copy)
   uint32_t pool_stride;
   uint32_t apply_smem;      // element application table staged in shared memory (u8 [NM][Q+1])
   uint32_t rmw;             // every G-mode template is >= 3 bytes long: edges merged by read-modify-write
@@ -76,10 +77,10 @@ __device__ __forceinline__ unsigned long long v4_globaltimer() {
 
 // ---- forward step: E = last entry (bits 0-15: absolute shared address of the
 // current row in this lane's copy, byte 2: bytes emitted, byte 3: flags)
-template <int K>
+template <int K, int LOG>
 __device__ __forceinline__ void v4_fstep(uint32_t cls_abs, uint32_t &E, uint32_t w, uint32_t &accL, uint32_t &accT) {
   const uint32_t c = lds_u8(__dp4a(w, 1u << (8 * K), cls_abs));
-  E = lds_u32((E & 0xFFFFu) + (c << 7));
+  E = lds_u32((E & 0xFFFFu) + (c << LOG));
   accL = __dp4a(E, 0x00010000u, accL);
   accT = mad_hi_u32(E, 2u, accT);
 }
@@ -284,25 +285,28 @@ __device__ __noinline__ void v4_slow_write(const PhaseDev &P, const FastDev &F, 
 #ifndef KEX_V4_THREADS
 #define KEX_V4_THREADS 1024
 #endif
-template <bool REGS>
+// LOG: log2 of the entry stride of the transition table.  7 = one copy of every entry per lane
+// (lane l only touches bank l: conflict-free); 6 = lanes l and l+16 share a copy (tables of up to
+// twice the size fit the 16-bit shared addresses, at the price of two-way conflicts).
+template <bool REGS, int LOG>
 __global__ void __launch_bounds__(KEX_V4_THREADS, 1)
 k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
         const uint16_t *__restrict__ samples, const uint16_t *__restrict__ blockpre,
         const uint16_t *__restrict__ chunk_start, const uint8_t *__restrict__ lam_end,
         unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl, uint8_t *__restrict__ out, size_t out_cap,
         unsigned long long out_off, uint32_t stage_bytes, uint32_t warp_bytes, uint32_t reccap, uint32_t force_exact) {
-  constexpr uint32_t STRIDE = 128u;
+  constexpr uint32_t STRIDE = 1u << LOG;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const uint32_t Q = P.Q, Q1 = Q + 1, C = P.C, C1 = C + 1u;
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_v3);
-  const uint32_t slot4 = lane * 4u;
+  const uint32_t slot4 = (lane * 4u) & (STRIDE - 1u);
   const uint32_t trans_abs = base + V.o_trans, cls_abs = base + V.o_cls, tpl_abs = base + V.o_tpl, pool_abs = base + V.o_pool;
   const uint32_t row_bytes = C1 * STRIDE;
-  if ((trans_abs & 127u) || trans_abs + Q1 * row_bytes > 65536u) __trap();
+  if ((trans_abs & 127u) || trans_abs + Q1 * row_bytes > 65536u || V.log != (uint32_t)LOG) __trap();
 
   // ---- tables (once per CTA).  Row q has C transition entries and, as entry C, G[q].
-  for (uint32_t i = tid; i < Q1 * C1 * 32u; i += blockDim.x) {
-    const uint32_t ent = i >> 5, s = i & 31u, q = ent / C1, c = ent - q * C1;
+  for (uint32_t i = tid; i < Q1 * C1 * (STRIDE / 4u); i += blockDim.x) {
+    const uint32_t ent = i >> (LOG - 2), s = i & (STRIDE / 4u - 1u), q = ent / C1, c = ent - q * C1;
     uint32_t v;
     if (c == C) {
       v = V.G[q];
@@ -444,10 +448,10 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         switch (j & 3) {
-          case 0: v4_fstep<0>(cls_abs, EA, w[j >> 2], cntA, nrA); v4_fstep<0>(cls_abs, EB, w[4 + (j >> 2)], cntB, nrB); break;
-          case 1: v4_fstep<1>(cls_abs, EA, w[j >> 2], cntA, nrA); v4_fstep<1>(cls_abs, EB, w[4 + (j >> 2)], cntB, nrB); break;
-          case 2: v4_fstep<2>(cls_abs, EA, w[j >> 2], cntA, nrA); v4_fstep<2>(cls_abs, EB, w[4 + (j >> 2)], cntB, nrB); break;
-          default: v4_fstep<3>(cls_abs, EA, w[j >> 2], cntA, nrA); v4_fstep<3>(cls_abs, EB, w[4 + (j >> 2)], cntB, nrB); break;
+          case 0: v4_fstep<0, LOG>(cls_abs, EA, w[j >> 2], cntA, nrA); v4_fstep<0, LOG>(cls_abs, EB, w[4 + (j >> 2)], cntB, nrB); break;
+          case 1: v4_fstep<1, LOG>(cls_abs, EA, w[j >> 2], cntA, nrA); v4_fstep<1, LOG>(cls_abs, EB, w[4 + (j >> 2)], cntB, nrB); break;
+          case 2: v4_fstep<2, LOG>(cls_abs, EA, w[j >> 2], cntA, nrA); v4_fstep<2, LOG>(cls_abs, EB, w[4 + (j >> 2)], cntB, nrB); break;
+          default: v4_fstep<3, LOG>(cls_abs, EA, w[j >> 2], cntA, nrA); v4_fstep<3, LOG>(cls_abs, EB, w[4 + (j >> 2)], cntB, nrB); break;
         }
         if (j & 1) {
           pr[j >> 1] = __byte_perm(pr[j >> 1], EA, 0x7610u);
@@ -461,7 +465,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       // exact end live set must be the one the table was built for
       bool bad = ((EA & 0xFFFFu) == fail_row) || ((EB & 0xFFFFu) == fail_row) ||
                  ((EA & 0xFFFFu) != trans_abs + sB * row_bytes + slot4);
-      if (REGS && lane == 31u) bad = bad || (lds_u32((EB & 0xFFFFu) + (C << 7)) != lam_tile);
+      if (REGS && lane == 31u) bad = bad || (lds_u32((EB & 0xFFFFu) + (C << LOG)) != lam_tile);
       gmode = !__any_sync(0xFFFFFFFFu, bad);
     }
     V4Slow sl;

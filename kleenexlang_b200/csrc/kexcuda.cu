@@ -987,7 +987,13 @@ static int load_v4(kex_program *p, PhaseHost &ph, const uint8_t *f, uint32_t fl,
   for (uint32_t q = 0; q < Q1; ++q)
     if (f[oG + q] != 0xFF && f[oG + q] >= NL) return KEX_ERR_BAD_BLOB;
   // shared-memory layout: the replicated transition table must be addressable with 16 bits
-  const size_t tbytes = (size_t)Q1 * (C + 1) * 128;
+  v.log = 7;
+  size_t tbytes = (size_t)Q1 * (C + 1) * 128;
+  // A table too large for per-lane copies stays on k3_emit: with two lanes per copy (LOG 6) the
+  // G-mode kernel measured no faster there (iso_datetime: 19.6 vs 19.0 ms per 3.94 GiB).  The
+  // variant is kept behind a knob for the tests.
+  if (tbytes + 2048 > 65536 && !getenv("KEX_V4_LOG6")) return KEX_OK;
+  if (getenv("KEX_V4_LOG6")) { v.log = 6; tbytes /= 2; }
   if (tbytes + 2048 > 65536) return KEX_OK;
   uint32_t sp = 0;
   v.o_trans = sp; sp += (uint32_t)tbytes;
@@ -1036,6 +1042,7 @@ static int load_v4(kex_program *p, PhaseHost &ph, const uint8_t *f, uint32_t fl,
   if (getenv("KEX_DEBUG"))
     fprintf(stderr, "kexcuda: v4 (G-mode) emit kernel: tables %u B, element table %s, template edges %s\n", v.o_warp,
             v.apply_smem ? "in shared memory" : "in global memory", v.rmw ? "merged" : "byte stores");
+  if (getenv("KEX_DEBUG") && v.log != 7) fprintf(stderr, "kexcuda: v4: entry stride %u B\n", 1u << v.log);
   return KEX_OK;
 }
 
@@ -1273,8 +1280,10 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
 #define V3_ATTR(L, R, T) cudaFuncSetAttribute(k3_emit<L, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
   V3_EACH(V3_ATTR)
 #undef V3_ATTR
-  cudaFuncSetAttribute(k4_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
-  cudaFuncSetAttribute(k4_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  cudaFuncSetAttribute(k4_emit<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  cudaFuncSetAttribute(k4_emit<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  cudaFuncSetAttribute(k4_emit<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
+  cudaFuncSetAttribute(k4_emit<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
   for (Ctx &c : p->cx) {
     if (cudaMallocHost((void **)&c.ctl_host, sizeof(FastCtl)) != cudaSuccess) { kex_free(p); return KEX_ERR_CUDA; }
@@ -1727,25 +1736,26 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     const uint32_t nwarp = nwork + 1u;
     const bool regs = NL > 1;
     int occ = 0;
-    if (regs) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_emit<true>, (int)(nwarp * 32u), smem4));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_emit<false>, (int)(nwarp * 32u), smem4));
+#define V4_EACH(X) X(true, 7) X(false, 7) X(true, 6) X(false, 6)
+#define V4_OCC(R, L)                                                                                                 \
+    if (regs == R && V.log == L) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_emit<R, L>, (int)(nwarp * 32u), smem4));
+    V4_EACH(V4_OCC)
+#undef V4_OCC
     if (occ < 1) return KEX_ERR_UNSUPPORTED;
     const size_t ngroups = (ntiles + nwork - 1) / nwork;
     size_t ctas = ngroups;
     if (ctas > (size_t)occ * (size_t)p->num_sms) ctas = (size_t)occ * (size_t)p->num_sms;
     if (p->timing) CK(cudaEventRecord(p->ev[4], st));
-    if (regs)
-      k4_emit<true><<<(unsigned)ctas, nwarp * 32u, smem4, st>>>(
-          P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,
-          (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,
-          (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,
+#define V4_LAUNCH(R, L)                                                                                              \
+    if (regs == R && V.log == L)                                                                                     \
+      k4_emit<R, L><<<(unsigned)ctas, nwarp * 32u, smem4, st>>>(                                                     \
+          P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,                   \
+          (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,  \
+          (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,                                \
           (unsigned long long)p->emit_out_off, ph.v4_stage, warp_bytes, ph.v4_reccap, force_exact);
-    else
-      k4_emit<false><<<(unsigned)ctas, nwarp * 32u, smem4, st>>>(
-          P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,
-          (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,
-          (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,
-          (unsigned long long)p->emit_out_off, ph.v4_stage, warp_bytes, ph.v4_reccap, force_exact);
+    V4_EACH(V4_LAUNCH)
+#undef V4_LAUNCH
+#undef V4_EACH
     p->launches++;
     if (p->timing) CK(cudaEventRecord(p->ev[5], st));
     CK(cudaGetLastError());

@@ -41,6 +41,9 @@ KIND_NOP, KIND_OUTSYM, KIND_OUTONLY, KIND_GENERAL = 0, 1, 2, 3
 PIECE_CONST, PIECE_SYM = 0, 1
 
 
+DEVICE_ACT_SLOTS = 32       # csrc/kex_act.cuh ACT_NSLOT
+
+
 class UnsupportedProgram(Exception):
     pass
 
@@ -342,6 +345,12 @@ def compile_kex(src: str, opt: int = 3, with_fast: bool = True, actions: bool = 
     weaker = {}                      # SSTs at weaker optimisation levels, built on demand
     for s in build_ssts(src, opt, actions=actions):
         if hasattr(s, "nregs"):
+            # the device interpreter shares ACT_NSLOT = 32 slots between the builders (one per stack
+            # height, at least the bottom one) and the registers (csrc/kex_act.cuh; kex_load rejects
+            # nregs + 1 > 32): refuse here, not with a binary that always fails at load
+            if s.nregs + 1 > DEVICE_ACT_SLOTS:
+                raise UnsupportedProgram("%d action registers exceed the %d slots of the device action interpreter"
+                                         % (s.nregs, DEVICE_ACT_SLOTS))
             phases.append(s)
             continue
         try:

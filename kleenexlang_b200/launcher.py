@@ -95,10 +95,23 @@ def main(blob_path, argv):
             return RETC_PRINT_USAGE
         i += 1
     t0 = time.time()
-    from .runtime import CompiledProgram
+    from .runtime import CompiledProgram, KexError, KEX_ERR_UNSUPPORTED
+    try:
+        return _run(blob_path, phase, do_timing, t0, CompiledProgram, KexError, KEX_ERR_UNSUPPORTED)
+    except KexError as e:                       # one line and exit 1, like the runtime's fatal errors
+        sys.stdout.buffer.flush()
+        sys.stderr.write("%s\n" % e)
+        return 1
+
+
+def _run(blob_path, phase, do_timing, t0, CompiledProgram, KexError, KEX_ERR_UNSUPPORTED):
     cp = CompiledProgram(open(blob_path, "rb").read())
     if phase:
-        cp.select_phase(phase)
+        try:
+            cp.select_phase(phase)
+        except KexError:
+            sys.stderr.write("Invalid phase: %d given\n" % phase)      # C.hs:59-69
+            return 1
     # inputs larger than one block are streamed block by block with bounded memory
     # (kex_stream_*); KEX_NO_STREAM=1 reads the whole input first
     block = int(os.environ.get("KEX_STREAM_BLOCK_MIB", "256")) << 20
@@ -106,13 +119,19 @@ def main(blob_path, argv):
     more = sys.stdin.buffer.read(1) if len(first) == block else b""
     streamable = bool(more) and not phase and not os.environ.get("KEX_NO_STREAM")
     if streamable:
-        from .runtime import KexError
         try:
             cp._check(cp._L.kex_stream_begin(cp._h))
         except KexError:
             streamable = False                  # multi-phase program or tables beyond the v3 kernels
     if streamable:
+        # Until the first output byte exists the fed blocks are kept: when the library reports that the
+        # input cannot be evaluated block by block (a register stays live across blocks: a second block
+        # would have to wait, KEX_ERR_UNSUPPORTED) the rest of stdin is read and everything is evaluated
+        # at once, as the reference binary would.
+        fed, wrote = [], [0]
+
         def blocks():
+            fed.append(first)
             yield first
             head = more
             while True:
@@ -120,8 +139,26 @@ def main(blob_path, argv):
                 head = b""
                 if not blk:
                     return
+                if not wrote[0]:
+                    fed.append(blk)
+                else:
+                    del fed[:]
                 yield blk
-        status, count = cp.run_stream(blocks(), sys.stdout.buffer.write)
+
+        def write(b):
+            wrote[0] += len(b)
+            sys.stdout.buffer.write(b)
+
+        try:
+            status, count = cp.run_stream(blocks(), write)
+        except KexError as e:
+            if e.code != KEX_ERR_UNSUPPORTED or wrote[0]:
+                raise
+            data = b"".join(fed) + sys.stdin.buffer.read()
+            cp.close()
+            cp = CompiledProgram(open(blob_path, "rb").read())
+            status, out, count = cp.run(data)
+            sys.stdout.buffer.write(out)
     else:
         data = first + more + (sys.stdin.buffer.read() if more else b"")
         status, out, count = cp.run(data)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # KEX_LIB: an alternative build of the same library (kernel experiments: scripts/build_exp.py)
 LIB_PATH = os.environ.get("KEX_LIB") or os.path.join(HERE, "libkexcuda.so")
 
-KEX_OK, KEX_ERR_OUT_CAP = 0, -3
+KEX_OK, KEX_ERR_OUT_CAP, KEX_ERR_UNSUPPORTED = 0, -3, -4
 ACCEPT, REJECT = 0, 1
 
 _lib = None

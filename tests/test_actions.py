@@ -152,3 +152,13 @@ def test_committed_action_vectors():
         assert (st == 0) == v["accept"]
         if v["accept"]:
             assert out == v["output"]
+
+
+def test_too_many_action_registers_refused_at_compile_time():
+    """The device interpreter has 32 slots for builders + registers: a program
+    with more registers is refused by compile_kex, not at kex_load."""
+    from kleenexlang_b200.kexprog import compile_kex, UnsupportedProgram
+    regs = ["r%d" % i for i in range(32)]
+    src = "main := " + " ".join("%s@/a/" % r for r in regs) + " " + " ".join("!%s" % r for r in regs) + "\n"
+    with pytest.raises(UnsupportedProgram):
+        compile_kex(src)

@@ -280,12 +280,12 @@ def test_v3_paths_forced(name, knob, monkeypatch):
     _check(prog, ssts, d[:1000000] + b"\x01" + d[1000001:])
 
 
-V4_PROGS = ["csv2json", "iso_datetime_to_json", "fastq2fasta"]
+V4_PROGS = ["csv2json", "fastq2fasta"]      # iso_datetime: 37 x 14 entries do not fit per-lane copies -> k3_emit
 
 
 @pytest.mark.parametrize("name", PROGS)
 @pytest.mark.parametrize("knob", [{}, {"KEX_V4_EXACT": "1"}, {"KEX_V4_STAGE": "256", "KEX_V4_RECCAP": "8"}, {"KEX_NO_V4": "1"},
-                                  {"KEX_V3_WORKERS": "3"}])
+                                  {"KEX_V3_WORKERS": "3"}, {"KEX_V4_LOG6": "1"}])
 def test_v4_paths_forced(name, knob, monkeypatch):
     """The G-mode emit kernel (kex_v4.cuh) and its rarely taken paths, forced:
     every tile evaluated exactly from the tables in global memory
@@ -312,7 +312,7 @@ def test_v4_paths_forced(name, knob, monkeypatch):
 
 @pytest.mark.parametrize("name", V4_PROGS)
 def test_v4_gmode_taken(name, monkeypatch, capfd):
-    """csv2json, iso_datetime and fastq2fasta have state-determined live sets:
+    """csv2json and fastq2fasta have state-determined live sets (and tables that fit):
     once G is learnt from the run, (nearly) every tile goes through the G-mode
     passes -- the library reports how many tiles it evaluated exactly."""
     from kleenexlang_b200.runtime import CompiledProgram

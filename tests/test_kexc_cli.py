@@ -18,9 +18,33 @@ ENV = dict(os.environ, PYTHONPATH=ROOT)
 def _compile(tmp_path, name, *flags):
     out = str(tmp_path / name)
     r = subprocess.run(KEXC + ["compile", os.path.join(PROGRAMS, name + ".kex"), "--out", out, *flags],
-                       capture_output=True, cwd=ROOT, env=ENV)
+                       capture_output=True, cwd=ROOT, env=dict(ENV, KEXC_LAUNCHER=LAUNCHER_KIND[0]))
     assert r.returncode == 0, r.stderr
     return out
+
+
+LAUNCHER_KIND = ["native"]
+
+
+@pytest.fixture(params=["native", "python"])
+def launcher_kind(request):
+    """`kexc compile --out bin` installs the native launcher (tools/kexrun.c: the C ABI bound
+    from C) by default, the interpreter-based one (launcher.py) with KEXC_LAUNCHER=python."""
+    LAUNCHER_KIND[0] = request.param
+    yield request.param
+    LAUNCHER_KIND[0] = "native"
+
+
+def test_native_launcher_is_a_binary(tmp_path):
+    out = _compile(tmp_path, "add-commas", "--quiet")
+    assert open(out, "rb").read(4) == b"\x7fELF"
+    assert os.path.exists(out + ".kexprog.lib") and os.path.exists(out + ".kexprog.desc")
+    LAUNCHER_KIND[0] = "python"
+    try:
+        out2 = _compile(tmp_path, "csv2json", "--quiet")
+    finally:
+        LAUNCHER_KIND[0] = "native"
+    assert open(out2, "rb").read(2) == b"#!"
 
 
 def test_compile_writes_blob_and_launcher(tmp_path):
@@ -70,14 +94,14 @@ def test_simulate_apache_log_config():
 
 
 @pytest.mark.gpu
-def test_compiled_binary_contract(tmp_path):
+def test_compiled_binary_contract(tmp_path, launcher_kind):
     vecs = [v for v in load_vectors() if not v["uses_registers"]][:12]
     for k, v in enumerate(vecs):
         src = tmp_path / ("p%d.kex" % k)
         src.write_text(v["program"], encoding="utf-8")
         out = str(tmp_path / ("p%d" % k))
         c = subprocess.run(KEXC + ["compile", str(src), "--out", out, "--opt", "0", "--la=false", "--quiet"],
-                           capture_output=True, cwd=ROOT, env=ENV)
+                           capture_output=True, cwd=ROOT, env=dict(ENV, KEXC_LAUNCHER=launcher_kind))
         if c.returncode == 1 and b"exceeds a limit" in c.stderr:
             continue                                          # > 32 simultaneously live registers
         assert c.returncode == 0, c.stderr
@@ -96,7 +120,7 @@ def test_compiled_binary_contract(tmp_path):
 
 
 @pytest.mark.gpu
-def test_launcher_streams_large_inputs(tmp_path):
+def test_launcher_streams_large_inputs(tmp_path, launcher_kind):
     """Inputs larger than one block go through kex_stream_* (bounded memory);
     with 1 MiB blocks a 6 MiB input streams and must equal the whole-input run."""
     from kleenexlang_b200 import workloads
@@ -130,7 +154,7 @@ def test_action_program_compile_and_simulate(tmp_path):
 
 
 @pytest.mark.gpu
-def test_action_program_binary(tmp_path):
+def test_action_program_binary(tmp_path, launcher_kind):
     out = str(tmp_path / "rev")
     r = subprocess.run(KEXC + ["compile", os.path.join(PROGRAMS, "actions", "reverse_items.kex"), "--out", out, "--quiet"],
                        capture_output=True, cwd=ROOT, env=ENV)
