@@ -95,8 +95,10 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------ reference arm
-def ref_binary():
-    p = os.path.join(ROOT, "oracle", "_ref", PROGRAM)
+def ref_binary(variant=""):
+    """oracle/_ref/<program>: `--act=false` (one process per instance); variant ".act": the
+    reference's default mode `--act=true` (oracle + action program, two processes per instance)."""
+    p = os.path.join(ROOT, "oracle", "_ref", PROGRAM + variant)
     return p if os.path.exists(p) else None
 
 
@@ -143,11 +145,11 @@ def make_reference_inputs(gen_name, sample_bytes, instances):
     return files, reps * len(block) * instances
 
 
-def run_reference_once(files):
+def run_reference_once(files, variant=""):
     """Times one concurrent pass of the reference's compiled C binary
     (oracle/_ref, emitted C + verbatim crt.c, `cc -O3 -D FLAG_WORDALIGNED`) over
     the files, stdout to /dev/null as bench/runningtime.sh:101 does."""
-    binp = ref_binary()
+    binp = ref_binary(variant)
     t0 = time.perf_counter()
     procs = [subprocess.Popen([binp], stdin=open(f, "rb"), stdout=subprocess.DEVNULL) for f in files]
     rcs = [p.wait() for p in procs]
@@ -156,10 +158,10 @@ def run_reference_once(files):
     return dt
 
 
-def time_reference(gen_name, sample_bytes, instances):
+def time_reference(gen_name, sample_bytes, instances, variant=""):
     files, total = make_reference_inputs(gen_name, sample_bytes, instances)
     try:
-        return run_reference_once(files), total
+        return run_reference_once(files, variant), total
     finally:
         for f in files:
             os.unlink(f)
@@ -181,7 +183,11 @@ def time_oracle_port(gen_name, sample_bytes):
 def cpu_baseline(gen_name, sample_bytes=1 << 30):
     if ref_binary():
         dt, nb = time_reference(gen_name, sample_bytes, 1)
-        return {"value": nb / GIB / dt, "unit": "GiB/s", "cores": 1, "kind": "reference",
+        variants = {"--act=false --la=false (1 process)": nb / GIB / dt}
+        if ref_binary(".act"):
+            dt2, nb2 = time_reference(gen_name, sample_bytes // 2, 1, ".act")
+            variants["--act=true --la=false --sb=false (reference default mode: oracle + action program, 2 processes)"] = nb2 / GIB / dt2
+        return {"value": nb / GIB / dt, "unit": "GiB/s", "cores": 1, "kind": "reference", "variants": variants,
                 "sample": "%d MiB synthetic input, 1 process of oracle/_ref/%s (emitted C + verbatim crt.c, "
                           "cc -O3 -D FLAG_WORDALIGNED, --opt 3 --la=false --act=false), stdin from /dev/shm, "
                           "stdout /dev/null" % (nb >> 20, PROGRAM)}

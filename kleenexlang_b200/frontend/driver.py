@@ -34,6 +34,17 @@ def build_ssts(src: str, opt: int = 3, actions: bool = False):
     return out
 
 
+def build_oracle_action_pipeline(src: str, opt: int = 3):
+    """-> [oracle SST, action SST, oracle SST, action SST, ...]: the phases of
+    the reference's default `kexc compile` (`--act=true`; two per pipeline
+    stage, C.hs:507-510), here with `--la=false --sb=false`."""
+    from .oracle_action import build_oracle_action_ssts
+    out = []
+    for t in build_transducers(src):
+        out.extend(build_oracle_action_ssts(t, opt))
+    return out
+
+
 def simulate_lockstep(src: str, data: bytes):
     """`kexc simulate --sim=lockstep` (Commands.hs:277-289): returns output
     bytes or None on reject."""

@@ -8,6 +8,7 @@ States are continuation stacks (tuples of reduced-grammar identifiers); the
 only final state is the empty stack.  Edge order encodes choice priority.
 
   sym[q] = [(byteset, func, q')]   func = "copy" | ("const", (out symbols...))
+                                   | ("code", byteset): oracle machines only (frontend/oracle_action.py)
   eps[q] = [((out symbols...), q')]
 
 Output symbols are ints (bytes) or action tuples ("push",)/("pop", r)/("write", r).
@@ -29,7 +30,7 @@ class FST:
     def has_actions(self):
         for es in self.sym.values():
             for _, f, _ in es:
-                if f != "copy" and any(not isinstance(y, int) for y in f[1]):
+                if f != "copy" and f[0] == "const" and any(not isinstance(y, int) for y in f[1]):
                     return True
         for es in self.eps.values():
             for ys, _ in es:

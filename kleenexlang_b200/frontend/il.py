@@ -9,8 +9,12 @@ function lowering of :135-145.  This is the data boundary both
 back ends consume: the reference-style C emitter under oracle/ and the CUDA
 table builder in kleenexlang_b200/kexprog.py.
 
+Programs of the default `--act=true` mode (frontend/oracle_action.py) also use
+tables (`AppendTblI`, IL.hs:37-39; built in Classes.hs:95-121): the oracle
+writes byte -> code digit, the action program code digit -> byte.
+
 Instructions (tagged tuples):
-  ("accept",) ("fail",) ("append", buf, constid) ("appendsym", buf, i)
+  ("accept",) ("fail",) ("append", buf, constid) ("appendsym", buf, i) ("appendtbl", buf, tableid, i)
   ("concat", dst, src) ("reset", buf) ("if", expr, block) ("goto", blockid)
   ("next", lo, hi, block) ("consume", k)
 Expressions:
@@ -96,7 +100,7 @@ def order_assignments(upd):
     return acc
 
 
-def _compile_assignment(var, atoms, cmap):
+def _compile_assignment(var, atoms, cmap, tmap=None):
     if atoms and atoms[0] == ("v", var):
         rest, pre = atoms[1:], []
     else:
@@ -106,6 +110,8 @@ def _compile_assignment(var, atoms, cmap):
             pre.append(("concat", var, a[1]))
         elif a[0] == "c":
             pre.append(("append", var, cmap[a[1]]))
+        elif a[0] == "t":
+            pre.append(("appendtbl", var, tmap[a[1]], 0))
         else:
             pre.append(("appendsym", var, 0))
     return pre
@@ -121,7 +127,17 @@ def compile_sst(sst) -> Program:
     for w in sst.final.values():
         consts.update(a[1] for a in w if a[0] == "c")
     cmap = {c: i for i, c in enumerate(sorted(consts))}
+    # tables in the Data.Map order of their range sets (`tmap`, SSTCompiler.hs:176-181); a table is
+    # identified here by its contents
+    tabs = set()
+    for es in sst.edges.values():
+        for _, upd, _ in es:
+            for w in upd.values():
+                tabs.update(a[1] for a in w if a[0] == "t")
+    tmap = {t: i for i, t in enumerate(sorted(tabs))}
+    action = getattr(sst, "action", False)
     prog = Program()
+    prog.tables = {i: t for t, i in tmap.items()}
     prog.constants = {i: c for c, i in cmap.items()}
     prog.stream_buffer = 0
     prog.buffers = sorted(sst.variables() | {0})
@@ -137,9 +153,14 @@ def compile_sst(sst) -> Program:
         for p, upd, q2 in trans:
             body = []
             for v, w in order_assignments(upd):
-                body.extend(_compile_assignment(v, w, cmap))
+                body.extend(_compile_assignment(v, w, cmap, tmap))
             body += [("consume", 1), ("goto", q2)]
-            test = ("and", ("gte", ("avail",), ("const", 1)), pred_list_to_expr([p], 0))
+            if action:
+                # ConstLab c -> next[0] == c, AnyLab -> no test (Classes.hs:94-101)
+                pe = ("true",) if BS.size(p) == 256 else ("eq", ("sym", 0), ("const", BS.to_list(p)[0]))
+            else:
+                pe = pred_list_to_expr([p], 0)
+            test = ("and", ("gte", ("avail",), ("const", 1)), pe)
             block.append(("if", test, body))
         block.append(("fail",))
         prog.blocks[q] = block

@@ -10,6 +10,7 @@ Commands.hs:126,171): every transition consumes exactly one byte.
 
 Trees:   ("tip", w, state) | ("fork", w, (children...))
 Atoms:   ("v", var) | ("c", (bytes...)) | ("f",)      ("f",) = append input byte
+         ("t", table)   append table[input byte] (oracle / action machines, frontend/oracle_action.py)
 Vars:    tuples giving the root->leaf path of the tree node that owns the
          register; () is the designated output register.  Tuple order is tree
          pre-order, so an ancestor always sorts before its descendants.
@@ -131,7 +132,13 @@ def _consume(fst, p, tree):
         if q2 in vis:
             return None
         vis.add(q2)
-        atom = ("f",) if f == "copy" else ("c", tuple(f[1]))
+        if f == "copy":
+            atom = ("f",)
+        elif f[0] == "code":                     # CodeArg p2 of an oracle machine: index of the byte in p2
+            from .oracle_action import code_table
+            atom = ("t", code_table(f[1]))
+        else:
+            atom = ("c", tuple(f[1]))
         return ("tip", (atom,), q2)
 
     return _reduce(_bind(tree, k))
@@ -221,7 +228,9 @@ def sst_from_fst(fst, max_states=200000):
             kappa, t2 = _abstract(tr)
             if BS.size(p) == 1:
                 b = BS.to_list(p)[0]
-                kappa = [(v, tuple(("c", (b,)) if a == ("f",) else a for a in w)) for v, w in kappa]
+                # `specialize` (Determinization.hs:190-206): a singleton predicate makes every function constant
+                kappa = [(v, tuple(("c", (b,)) if a == ("f",) else ("c", (a[1][b],)) if a[0] == "t" else a for a in w))
+                         for v, w in kappa]
             upd = {}
             for v, w in kappa:
                 assert v not in upd, "Inconsistent register update"
@@ -271,7 +280,7 @@ def _lift(rho, atoms):
                 amb = True
             else:
                 acc = acc + v
-        elif a[0] == "f":
+        elif a[0] in ("f", "t"):
             amb = True
         else:
             acc = acc + a[1]
@@ -367,6 +376,8 @@ def run_sst(sst, data: bytes):
                     buf += regs[a[1]]
                 elif a[0] == "c":
                     buf += bytes(a[1])
+                elif a[0] == "t":
+                    buf.append(a[1][b])
                 else:
                     buf.append(b)
             new[v] = bytes(buf)

@@ -8,7 +8,12 @@ where it lies, compiled with the reference's command line
 (git-ignored, but shipped to the GPU box).  Requires /root/reference; on a
 box without it the prebuilt binaries are used as they are.
 
-usage: python oracle/build_ref.py [--opt N] [prog.kex ...]
+With --act the programs are compiled in the reference's default mode
+(`--act=true`: an oracle and an action program per pipeline stage, two
+processes per stage, tables; frontend/oracle_action.py) as
+`oracle/_ref/<program>.act`; `--la=false --sb=false` in both modes.
+
+usage: python oracle/build_ref.py [--opt N] [--act] [prog.kex ...]
 """
 import os
 import subprocess
@@ -21,16 +26,17 @@ CRT = "/root/reference/crt/crt.c"
 REF_DIR = os.path.join(HERE, "_ref")
 
 
-def build_one(kex_path, opt=3, out_dir=REF_DIR, name=None, keep_c=False):
-    from kleenexlang_b200.frontend.driver import build_ssts
+def build_one(kex_path, opt=3, out_dir=REF_DIR, name=None, keep_c=False, act=False):
+    from kleenexlang_b200.frontend.driver import build_ssts, build_oracle_action_pipeline
     from kleenexlang_b200.frontend.il import compile_sst
     from oracle.emit_c import render_c
     src = open(kex_path, encoding="utf-8").read()
-    progs = [compile_sst(s) for s in build_ssts(src, opt)]
-    ctext = render_c(progs, open(CRT).read(), info="%s --opt %d --la=false --act=false" % (
-        os.path.basename(kex_path), opt))
+    ssts = build_oracle_action_pipeline(src, opt) if act else build_ssts(src, opt)
+    progs = [compile_sst(s) for s in ssts]
+    ctext = render_c(progs, open(CRT).read(), info="%s --opt %d --la=false --act=%s%s" % (
+        os.path.basename(kex_path), opt, "true" if act else "false", " --sb=false" if act else ""))
     os.makedirs(out_dir, exist_ok=True)
-    name = name or os.path.splitext(os.path.basename(kex_path))[0]
+    name = name or os.path.splitext(os.path.basename(kex_path))[0] + (".act" if act else "")
     out = os.path.join(out_dir, name)
     if keep_c:
         open(out + ".c", "w").write(ctext)
@@ -48,11 +54,15 @@ def have_reference():
 def main(argv):
     opt = 3
     paths = []
+    act = None
     i = 0
     while i < len(argv):
         if argv[i] == "--opt":
             opt = int(argv[i + 1])
             i += 2
+        elif argv[i] == "--act":
+            act = True
+            i += 1
         else:
             paths.append(argv[i])
             i += 1
@@ -63,7 +73,14 @@ def main(argv):
         pdir = os.path.join(ROOT, "programs")
         paths = sorted(os.path.join(pdir, f) for f in os.listdir(pdir) if f.endswith(".kex"))
     for p in paths:
-        print("built", build_one(p, opt))
+        if act is None or not act:
+            print("built", build_one(p, opt))
+        if act is None or act:
+            # the default-mode binary as well (programs with register actions only exist in this mode)
+            try:
+                print("built", build_one(p, opt, act=True))
+            except (ValueError, AssertionError, NotImplementedError) as e:
+                print("skipped %s --act=true: %s" % (os.path.basename(p), e))
     return 0
 
 

@@ -54,6 +54,12 @@ def _instr(prog, ins, phase, ind):
         if ins[1] == sb:
             return [pad + "outputarray(const_%d_%d,%d);" % (phase, ins[2], n)]
         return [pad + "appendarray(&buf_%d,const_%d_%d,%d);" % (ins[1], phase, ins[2], n)]
+    if k == "appendtbl":
+        # prettyAppendTbl (C.hs:232-251): one 8-bit cell per table entry (digit size 1)
+        arg = "tbl%d[%d][next[%d]]" % (phase, ins[2], ins[3])
+        if ins[1] == sb:
+            return [pad + "outputconst(%s,8);" % arg]
+        return [pad + "append(&buf_%d,%s,8);" % (ins[1], arg)]
     if k == "appendsym":
         if ins[1] == sb:
             return [pad + "outputconst(next[%d],8);" % ins[2]]
@@ -86,8 +92,18 @@ def render_c(programs, crt_text, info="kleenex-b200 oracle build"):
     uint8_t buffer units (C.hs:495-520)."""
     n = len(programs)
     out = ["", "#define NUM_PHASES %d" % n, "#define BUFFER_UNIT_T uint8_t", crt_text, ""]
-    for _ in programs:
-        out.append("/* no tables */")
+    for ph, p in enumerate(programs, 1):
+        # prettyTableDecl (C.hs:413-430); cells as prettyTableExpr prints them, eight to a line
+        if not p.tables:
+            out.append("/* no tables */")
+            continue
+        size = max(len(t) for t in p.tables.values())
+        rows = []
+        for tid in sorted(p.tables):
+            t = p.tables[tid]
+            lines = [", ".join("0x%02x" % c for c in t[i:i + 8]) for i in range(0, len(t), 8)]
+            rows.append("{" + ",\n".join(lines) + "}")
+        out.append("const uint8_t tbl%d[%d][%d] =\n{%s};" % (ph, len(p.tables), size, ",\n".join(rows)))
     bufs = sorted({b for p in programs for b in p.buffers})
     for b in bufs:
         out.append("buffer_t buf_%d;" % b)

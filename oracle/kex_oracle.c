@@ -21,6 +21,8 @@
  *              per transition: pred[8] (256-bit set), dest, nassign,
  *                              per assignment (execution order): var, natoms, atoms...
  *   atom: 0 var | 1 len bytes(padded to words) | 2 (current input byte)
+ *         | 3 table[256] (64 words): table[current input byte] -- AppendTblI of the
+ *           oracle / action programs of the default --act=true mode (C.hs:232-251)
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -40,6 +42,7 @@ static const uint32_t *skip_atoms(const uint32_t *p, uint32_t n) {
     uint32_t t = *p++;
     if (t == 0) p++;
     else if (t == 1) { uint32_t l = *p++; p += (l + 3) / 4; }
+    else if (t == 3) p += 64;
   }
   return p;
 }
@@ -87,8 +90,10 @@ static void run_atoms(const uint32_t *p, uint32_t n, uint32_t self, int to_strea
       if (to_stream) { for (uint32_t k = 0; k < l; ++k) out_byte(o, c[k]); }                      /* outputarray() */
       else { buf_reserve(dst, dst->len + l); memcpy(dst->data + dst->len, c, l); dst->len += l; }  /* appendarray() */
     } else {
-      if (to_stream) out_byte(o, sym);                                                             /* outputconst(next[0],8) */
-      else { buf_reserve(dst, dst->len + 1); dst->data[dst->len++] = sym; }                        /* append() */
+      uint8_t w = sym;
+      if (t == 3) { w = ((const uint8_t *)p)[sym]; p += 64; }                                      /* tblP[t][next[0]] */
+      if (to_stream) out_byte(o, w);                                                               /* outputconst(next[0],8) */
+      else { buf_reserve(dst, dst->len + 1); dst->data[dst->len++] = w; }                          /* append() */
     }
   }
 }

@@ -28,6 +28,8 @@ def _atoms(w):
             bs = bytes(a[1])
             pad = bs + b"\0" * ((-len(bs)) % 4)
             out += [1, len(bs)] + list(struct.unpack("<%dI" % (len(pad) // 4), pad))
+        elif a[0] == "t":
+            out += [3] + list(struct.unpack("<64I", bytes(a[1])))
         else:
             out += [2]
     return out

@@ -83,3 +83,56 @@ def test_oracle_vs_reference_binary(prog, gen):
 def test_oracle_vs_reference_binary_apache():
     d = sample("apache_sample.log")
     assert oracle_run(build_ssts(program_source("apache_log")), d)[:2] == _ref("apache_log", d)[:2]
+
+
+# ---- the reference's default mode (--act=true): oracle + action program per stage
+ALL_VECS = load_vectors()
+
+
+@pytest.mark.parametrize("opt", [0, 3])
+@pytest.mark.parametrize("v", ALL_VECS, ids=[v["name"] for v in ALL_VECS])
+def test_oracle_action_pipeline_golden(v, opt):
+    """Every golden vector of the reference -- the programs with register
+    actions included -- through the restated oracle/action split
+    (frontend/oracle_action.py: OracleMachine.hs, ActionMachine.hs,
+    ActionSST.hs) evaluated by the C oracle with table atoms."""
+    from kleenexlang_b200.frontend.driver import build_oracle_action_pipeline
+    phases = build_oracle_action_pipeline(v["program"], opt)
+    assert len(phases) % 2 == 0
+    st, out, _ = oracle_run(phases, v["input"])
+    assert st == 0 and vec_matches(v, out)
+
+
+def test_oracle_code_stream_shape():
+    """One code byte per copied byte of a non-singleton range set and per n-way
+    choice, nothing for singleton sets and suppressed reads
+    (OracleMachine.hs:52-61); the action program decodes it through tables."""
+    from kleenexlang_b200.frontend.driver import build_oracle_action_pipeline
+    from kleenexlang_b200.frontend.sst import run_sst
+    o, a = build_oracle_action_pipeline('main := (/[a-c]/ | ~/x/ "X")* /;/\n', 0)
+    ok, code, _ = run_sst(o, b"bxa;")
+    # loop choice (0 = iterate, 1 = leave) and arm choice (0 = class, 1 = x) per item; [a-c] index; ';' is a singleton
+    assert ok and code == bytes([0, 0, 1, 0, 1, 0, 0, 0, 1])
+    ok, out, _ = run_sst(a, code)
+    assert ok and out == b"bXa;"
+    assert any(at[0] == "t" for es in o.edges.values() for _, upd, _ in es for w in upd.values() for at in w)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "csv2json.act")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("prog,gen", CASES)
+def test_default_mode_reference_binary(prog, gen):
+    """oracle/_ref/<prog>.act = the reference's default two-process binary
+    (emitted oracle + action C programs with tables, verbatim crt.c): same
+    output as the direct binary and the oracle on accepted inputs; on a reject
+    the oracle phase reports the same `count`."""
+    from kleenexlang_b200.frontend.driver import build_oracle_action_pipeline
+    src = program_source(prog)
+    data = workloads.GENERATORS[gen](300000, seed=12).tobytes()
+    rc, out, _ = _ref(prog + ".act", data)
+    assert (rc, out) == _ref(prog, data)[:2] == oracle_run(build_ssts(src), data)[:2]
+    assert oracle_run(build_oracle_action_pipeline(src), data)[:2] == (0, out)
+    bad = data[:150001] + b"\x01" + data[150001:]
+    st, _, cnt = oracle_run(build_ssts(src), bad)
+    rc, _, err = _ref(prog + ".act", bad)
+    if st:
+        assert rc == 1 and err.startswith(("Match error at input symbol %d!" % cnt).encode())
