@@ -258,6 +258,6 @@ def build_oracle_action_ssts(fst, opt=3):
     (compileOracleAction, Commands.hs:204-244): (oracle SST, action SST)."""
     from .sst import sst_from_fst, optimize
     o = optimize(sst_from_fst(oracle_fst(fst)), opt)
-    a = optimize(action_to_sst(action_fst(fst)), opt)
+    a = optimize(action_to_sst(action_fst(fst)), opt, persistent=True)
     a.action = True
     return o, a

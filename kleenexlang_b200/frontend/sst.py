@@ -293,14 +293,30 @@ def _lub(a, b):
     return a
 
 
-def optimize(sst, level=3):
+def optimize(sst, level=3, persistent=False):
     """Constant propagation of registers (`optimize`, SymbolicSST.hs:323-331;
     abstract interpretation :273-321).  level 0 = off; 1-2 = weak variant
-    (a register that reads itself is ambiguous); 3 = full."""
+    (a register that reads itself is ambiguous); 3 = full.
+
+    `persistent`: for SSTs whose updates leave registers untouched by omission
+    (action SSTs, ActionSST.hs: `interp` only names the registers an action
+    touches).  The reference's rule deletes every update of a register that is
+    statically known in the destination state; if that register later reaches,
+    without an update, a state where it is no longer known, its buffer still
+    holds the value from before the deleted update (found on
+    bench/kleenex/src/drex_align-bibtex.kex: the reset of a popped builder is
+    lost, scripts/gen_reference_action_vectors.py).  Path-tree SSTs name every
+    live register in every update, so this never happens there; with
+    `persistent` the known value is written back on such an edge."""
     if level <= 0:
         return sst
     weak = level < 3
     gamma = {q: {} for q in range(sst.nstates)}
+    if persistent:
+        # every buffer starts empty (`init`, C.hs:470-484) and a register may be read before any
+        # action has assigned it (`!r` before `r@...`): the reference starts from "nothing known",
+        # which lets a constant assigned on one path stand for the untouched register of another
+        gamma[sst.initial] = {v: () for v in range(1, sst.nvars)}
     states = set(range(sst.nstates))
     while states:
         acc = {}
@@ -345,7 +361,12 @@ def optimize(sst, level=3):
         new = []
         for p, kappa, q2 in es:
             exact = {k for k, v in gamma[q2].items() if v != _AMB}
-            new.append((p, {k: apply(gamma[q], w) for k, w in kappa.items() if k not in exact}, q2))
+            upd = {k: apply(gamma[q], w) for k, w in kappa.items() if k not in exact}
+            if persistent:
+                for k, v in gamma[q].items():
+                    if v != _AMB and k not in exact and k not in kappa:
+                        upd[k] = (("c", v),) if v else ()
+            new.append((p, upd, q2))
         edges[q] = new
     final = {q: apply(gamma[q], w) for q, w in sst.final.items()}
     return SST(sst.nstates, edges, sst.initial, final, sst.nvars)

@@ -107,3 +107,23 @@ def test_committed_action_vectors_on_gpu():
         assert (st == 0) == v["accept"], v["program"]
         if v["accept"]:
             assert out == v["output"], v["program"]
+
+
+from test_actions import REF_ACTION_VECS
+
+
+@pytest.mark.parametrize("v", REF_ACTION_VECS, ids=[v["name"] for v in REF_ACTION_VECS])
+def test_reference_register_programs_gpu(v):
+    """The reference's own benchmark programs with register actions, executed
+    by the CUDA path (transducer phase + action-interpreter kernels) on the
+    committed vectors (tests/golden/reference_action_vectors.json)."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    prog = CompiledProgram(compile_kex(v["program"]))
+    assert prog.run(v["input"])[:2] == (0, v["output"])
+    # and tiled: most of these grammars are record* -- where tiling keeps the input in the
+    # language the output tiles as well (checked against the oracle, not assumed)
+    big = v["input"] * 50
+    est, eout, _ = oracle_run(build_ssts(v["program"], 3, actions=True), big)
+    got = prog.run(big)
+    assert got[0] == est and (est != 0 or got[1] == eout)
+    prog.close()
