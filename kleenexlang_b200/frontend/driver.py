@@ -34,15 +34,21 @@ def build_ssts(src: str, opt: int = 3, actions: bool = False):
     return out
 
 
-def build_oracle_action_pipeline(src: str, opt: int = 3):
+def build_oracle_action_pipeline(src: str, opt: int = 3, lookahead: bool = False):
     """-> [oracle SST, action SST, oracle SST, action SST, ...]: the phases of
     the reference's default `kexc compile` (`--act=true`; two per pipeline
-    stage, C.hs:507-510), here with `--la=false --sb=false`."""
+    stage, C.hs:507-510) with `--sb=false`; `lookahead` = `--la`."""
     from .oracle_action import build_oracle_action_ssts
     out = []
     for t in build_transducers(src):
-        out.extend(build_oracle_action_ssts(t, opt))
+        out.extend(build_oracle_action_ssts(t, opt, lookahead))
     return out
+
+
+def build_lookahead_ssts(src: str, opt: int = 3):
+    """`kexc compile --act=false --la=true`: direct SSTs whose transitions may
+    test several symbols (longest deterministic prefixes, SymbolicFST.hs:262-312)."""
+    return [optimize(sst_from_fst(t, lookahead=True), opt) for t in build_transducers(src)]
 
 
 def simulate_lockstep(src: str, data: bytes):

@@ -111,14 +111,44 @@ def _compile_assignment(var, atoms, cmap, tmap=None):
         elif a[0] == "c":
             pre.append(("append", var, cmap[a[1]]))
         elif a[0] == "t":
-            pre.append(("appendtbl", var, tmap[a[1]], 0))
+            pre.append(("appendtbl", var, tmap[a[1]], a[2] if len(a) > 2 else 0))
         else:
-            pre.append(("appendsym", var, 0))
+            pre.append(("appendsym", var, a[1] if len(a) > 1 else 0))
     return pre
 
 
+def kvtree(xs):
+    """`kvtree` / `lcp` (SSTCompiler.hs:37-55): tests with a common prefix share a
+    root; -> (action or None, [(prefix tuple, subtree)]) with the groups in the
+    Data.Map order of their first predicate."""
+    here = [b for ps, b in xs if not ps]
+    if len(here) > 1:
+        raise ValueError("Ambiguous transition map")
+    groups = {}
+    for ps, b in xs:
+        if ps:
+            groups.setdefault(ps[0], []).append((ps, b))
+
+    def lcp(ys):
+        if not ys or any(not ps for ps, _ in ys):
+            return (), ys
+        h = ys[0][0][0]
+        if all(ps[0] == h for ps, _ in ys):
+            p, rest = lcp([(ps[1:], b) for ps, b in ys])
+            return (h,) + p, rest
+        return (), ys
+
+    out = []
+    for first in sorted(groups, key=BS.to_ranges):
+        # fromListWith (++) prepends: the group is in reverse order of insertion -- irrelevant to lcp
+        pre, rest = lcp(groups[first])
+        out.append((pre, kvtree(rest)))
+    return (here[0] if here else None, out)
+
+
 def compile_sst(sst) -> Program:
-    """`compile` (SSTCompiler.hs:158-200) for single-symbol direct SSTs."""
+    """`compile` (SSTCompiler.hs:158-200): single-symbol SSTs (direct, oracle,
+    action) and lookahead SSTs (`sst.la`: predicate tuples, nested tests)."""
     consts = set()
     for es in sst.edges.values():
         for _, upd, _ in es:
@@ -133,7 +163,7 @@ def compile_sst(sst) -> Program:
     for es in sst.edges.values():
         for _, upd, _ in es:
             for w in upd.values():
-                tabs.update(a[1] for a in w if a[0] == "t")
+                tabs.update(a[1] for a in w if a[0] == "t")       # ("t", table[, index])
     tmap = {t: i for i, t in enumerate(sorted(tabs))}
     action = getattr(sst, "action", False)
     prog = Program()
@@ -142,12 +172,36 @@ def compile_sst(sst) -> Program:
     prog.stream_buffer = 0
     prog.buffers = sorted(sst.variables() | {0})
     prog.init_block = sst.initial
+    la = getattr(sst, "la", False)
+
+    def transitions(i, tree):
+        """compileTransitions (SSTCompiler.hs:113-130): deeper tests first, then this node's own action."""
+        action_, tests = tree
+        block = []
+        for ps, sub in tests:
+            test = ("and", ("gte", ("avail",), ("const", i + len(ps))), pred_list_to_expr(list(ps), i))
+            block.append(("if", test, transitions(i + len(ps), sub)))
+        if action_ is not None:
+            upd, q2 = action_
+            for v, w in order_assignments(upd):
+                block.extend(_compile_assignment(v, w, cmap, tmap))
+            block += [("consume", i), ("goto", q2)]
+        return block
+
     for q in range(sst.nstates):
         fin = sst.final.get(q)
         if fin is None:
             eof = [("fail",)]
         else:
             eof = _compile_assignment(0, fin, cmap) + [("accept",)]
+        if la:
+            es = sst.edges.get(q, ())
+            lens = [len(ps) for ps, _, _ in es] or [1]
+            block = [("next", min(lens), max(lens), eof)]          # compileState, SSTCompiler.hs:138-156
+            block += transitions(0, kvtree([(tuple(ps), (upd, q2)) for ps, upd, q2 in es]))
+            block.append(("fail",))
+            prog.blocks[q] = block
+            continue
         block = [("next", 1, 1, eof)]
         trans = sorted(sst.edges.get(q, ()), key=lambda e: BS.to_ranges(e[0]))
         for p, upd, q2 in trans:

@@ -253,11 +253,13 @@ def _state_key(q):
     return tuple(q)
 
 
-def build_oracle_action_ssts(fst, opt=3):
+def build_oracle_action_ssts(fst, opt=3, lookahead=False):
     """One pipeline stage as the reference's default mode compiles it
-    (compileOracleAction, Commands.hs:204-244): (oracle SST, action SST)."""
+    (compileOracleAction, Commands.hs:204-244): (oracle SST, action SST).
+    `lookahead` (`--la`) only concerns the oracle (Commands.hs:126: the action
+    machine is deterministic and never looks ahead)."""
     from .sst import sst_from_fst, optimize
-    o = optimize(sst_from_fst(oracle_fst(fst)), opt)
+    o = optimize(sst_from_fst(oracle_fst(fst), lookahead=lookahead), opt)
     a = optimize(action_to_sst(action_fst(fst)), opt, persistent=True)
     a.action = True
     return o, a

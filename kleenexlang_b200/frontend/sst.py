@@ -118,7 +118,15 @@ def _eof(fst, tree):
     return _reduce(_bind(tree, k))
 
 
-def _consume(fst, p, tree):
+def _kill(tree, kills):
+    """killTree (Determinization.hs:160-163): drop the tips in `kills`."""
+    return _reduce(_bind(tree, lambda q: None if q in kills else ("tip", (), q)))
+
+
+def _consume(fst, p, tree, idx=0):
+    """consumeTree (Determinization.hs:152-158); idx = position of the symbol in the
+    lookahead window (`inj i`, :221-223): atoms ("f",) / ("t", table) for idx 0,
+    ("f", idx) / ("t", table, idx) further in."""
     vis = set()
 
     def k(q):
@@ -133,10 +141,10 @@ def _consume(fst, p, tree):
             return None
         vis.add(q2)
         if f == "copy":
-            atom = ("f",)
+            atom = ("f",) if idx == 0 else ("f", idx)
         elif f[0] == "code":                     # CodeArg p2 of an oracle machine: index of the byte in p2
             from .oracle_action import code_table
-            atom = ("t", code_table(f[1]))
+            atom = ("t", code_table(f[1])) if idx == 0 else ("t", code_table(f[1]), idx)
         else:
             atom = ("c", tuple(f[1]))
         return ("tip", (atom,), q2)
@@ -202,8 +210,71 @@ class SST:
         return vs
 
 
-def sst_from_fst(fst, max_states=200000):
-    """sstFromFST in singleton mode (Determinization.hs:231-257)."""
+# ---- lookahead (`--la=true`): longest deterministic prefixes as multi-symbol tests
+def _right_input_closure(fst, q):
+    """rightInputClosure (SymbolicFST.hs:282-297): states without epsilon edges reachable over epsilon edges."""
+    out, vis = set(), set()
+
+    def go(q):
+        es = fst.eps.get(q)
+        if not es:
+            out.add(q)
+            return
+        for _, q2 in es:
+            if q2 not in vis:
+                vis.add(q2)
+                go(q2)
+
+    go(q)
+    return out
+
+
+def _step_all(fst, p, ctx):
+    """stepAll (SymbolicFST.hs:273-280)."""
+    out = set()
+    for q in ctx:
+        for p2, _, q2 in fst.sym.get(q, ()):
+            if BS.is_subset(p, p2):
+                out |= _right_input_closure(fst, q2)
+    return out
+
+
+def _ldp(fst, ctx, q, limit=64):
+    """ldp (SymbolicFST.hs:262-271): the longest deterministic prefix of state q in
+    the context of the state set ctx."""
+    out = []
+    ctx = set(ctx)
+    while len(out) < limit:
+        es = fst.sym.get(q, ())
+        if len(es) != 1:
+            break
+        p, _, q2 = es[0]
+        if p not in coarsest_predicate_set(fst, sorted(ctx)):
+            break
+        out.append(p)
+        ctx = _step_all(fst, p, ctx)
+        q = q2
+    return tuple(out)
+
+
+def prefix_tests(fst, singleton_mode, states):
+    """prefixTests (SymbolicFST.hs:299-312) -> [(predicate list, killed states)]."""
+    ldps = [] if singleton_mode else [(_ldp(fst, states, q), q) for q in states]
+    tests = {(p,) for p in coarsest_predicate_set(fst, states)} | {ps for ps, _ in ldps}
+
+    def entails(t, ps):
+        return len(ps) <= len(t) and all(a == b for a, b in zip(t, ps))
+
+    key = lambda t: tuple(BS.to_ranges(p) for p in t)
+    return [(t, {q for ps, q in ldps if not entails(t, ps)}) for t in sorted(tests, key=key)]
+
+
+def sst_from_fst(fst, max_states=200000, lookahead=False):
+    """sstFromFST (Determinization.hs:231-257).  `lookahead` = `--la=true`
+    (singletonMode = not la, Commands.hs:126,171): transitions may then test
+    several symbols (SST.la is set, edges carry predicate tuples)."""
+    if lookahead:
+        return _sst_from_fst_la(fst, max_states)
     if fst.has_actions():
         raise ValueError("Transducer contains action symbols - direct SST generation not supported")
     init = ("tip", (), fst.initial)
@@ -260,6 +331,74 @@ def sst_from_fst(fst, max_states=200000):
             (p, {vid[v]: ren(w) for v, w in upd.items()}, index[t2]))
     final = {index[t]: ren(w) for t, w in finals.items()}
     return SST(len(order), edges, 0, final, len(vid))
+
+
+def _sst_from_fst_la(fst, max_states):
+    if fst.has_actions():
+        raise ValueError("Transducer contains action symbols - direct SST generation not supported")
+    init = ("tip", (), fst.initial)
+    index = {init: 0}
+    order = [init]
+    trans = []
+    finals = {}
+    i = 0
+    while i < len(order):
+        t = order[i]
+        i += 1
+        tcl = _closure(fst, _unabstract_outputs(t))
+        fin = _eof(fst, tcl)
+        if fin is not None and fin[0] == "tip":
+            finals[t] = normalize_update(fin[1])
+        if tcl is None:
+            continue
+        for ps, kills in prefix_tests(fst, False, _tflat(tcl)):
+            if not ps:
+                continue
+            tr = _kill(tcl, kills)
+            for k, p in enumerate(ps):          # consumeTreeMany (Determinization.hs:213-229)
+                tr = _closure(fst, _consume(fst, p, _closure(fst, tr), k))
+            if tr is None:
+                continue
+            kappa, t2 = _abstract(tr)
+            if all(BS.size(p) == 1 for p in ps):
+                # `specialize` (Determinization.hs:190-206): a test of singletons makes every function constant
+                bs = [BS.to_list(p)[0] for p in ps]
+
+                def const(a):
+                    if a[0] == "f":
+                        return ("c", (bs[a[1] if len(a) > 1 else 0],))
+                    if a[0] == "t":
+                        return ("c", (a[1][bs[a[2] if len(a) > 2 else 0]],))
+                    return a
+                kappa = [(v, tuple(const(a) for a in w)) for v, w in kappa]
+            upd = {}
+            for v, w in kappa:
+                assert v not in upd, "Inconsistent register update"
+                upd[v] = normalize_update(w)
+            if t2 not in index:
+                if len(order) >= max_states:
+                    raise MemoryError("SST exceeds %d states" % max_states)
+                index[t2] = len(order)
+                order.append(t2)
+            trans.append((t, ps, upd, t2))
+    vs = {()}
+    for _, _, upd, _ in trans:
+        vs.update(upd.keys())
+        for w in upd.values():
+            vs.update(a[1] for a in w if a[0] == "v")
+    for w in finals.values():
+        vs.update(a[1] for a in w if a[0] == "v")
+    vid = {v: k for k, v in enumerate(sorted(vs))}
+
+    def ren(w):
+        return tuple(("v", vid[a[1]]) if a[0] == "v" else a for a in w)
+
+    edges = {}
+    for t, ps, upd, t2 in trans:
+        edges.setdefault(index[t], []).append((ps, {vid[v]: ren(w) for v, w in upd.items()}, index[t2]))
+    sst = SST(len(order), edges, 0, {index[t]: ren(w) for t, w in finals.items()}, len(vid))
+    sst.la = True
+    return sst
 
 
 # ------------------------------------------------------------- optimisation
@@ -369,7 +508,11 @@ def optimize(sst, level=3, persistent=False):
             new.append((p, upd, q2))
         edges[q] = new
     final = {q: apply(gamma[q], w) for q, w in sst.final.items()}
-    return SST(sst.nstates, edges, sst.initial, final, sst.nvars)
+    out = SST(sst.nstates, edges, sst.initial, final, sst.nvars)
+    for flag in ("la", "action"):
+        if getattr(sst, flag, False):
+            setattr(out, flag, True)
+    return out
 
 
 # ---------------------------------------------------------------- simulator
@@ -377,6 +520,8 @@ def run_sst(sst, data: bytes):
     """Sequential SST semantics with *persistent* registers, i.e. what the
     emitted C program computes (registers absent from an update keep their
     value).  Returns (accepted, output, consumed)."""
+    if getattr(sst, "la", False):
+        return _run_sst_la(sst, data)
     regs = {v: b"" for v in range(sst.nvars)}
     out = bytearray()
     q = sst.initial
@@ -410,3 +555,51 @@ def run_sst(sst, data: bytes):
     for a in sst.final[q]:
         out += regs[a[1]] if a[0] == "v" else bytes(a[1])
     return True, bytes(out), len(data)
+
+
+def _run_sst_la(sst, data: bytes):
+    """Lookahead SSTs as the emitted C runs them: the longest matching test wins
+    (`findTrans`, SymbolicSST.hs:441-446 = the nesting of `kvtree`,
+    SSTCompiler.hs:37-55), and the end-of-input branch is taken as soon as fewer
+    than minL symbols remain (`readnext(minL, maxL)`, crt/crt.c:293-312;
+    SSTCompiler.hs:138-146) -- a final state then accepts with unread input."""
+    regs = {v: b"" for v in range(sst.nvars)}
+    out = bytearray()
+    q = sst.initial
+    i, n = 0, len(data)
+    while True:
+        es = sst.edges.get(q, ())
+        min_l = min((len(ps) for ps, _, _ in es), default=1)
+        if n - i < min_l:
+            break
+        best = None
+        for ps, upd, q2 in es:
+            k = len(ps)
+            if k <= n - i and all((p >> data[i + j]) & 1 for j, p in enumerate(ps)) and (best is None or k > best[0]):
+                best = (k, upd, q2)
+        if best is None:
+            return False, bytes(out), i
+        k, upd, q2 = best
+        new = {}
+        for v, atoms in upd.items():
+            buf = bytearray()
+            for a in atoms:
+                if a[0] == "v":
+                    buf += regs[a[1]]
+                elif a[0] == "c":
+                    buf += bytes(a[1])
+                elif a[0] == "t":
+                    buf.append(a[1][data[i + (a[2] if len(a) > 2 else 0)]])
+                else:
+                    buf.append(data[i + (a[1] if len(a) > 1 else 0)])
+            new[v] = bytes(buf)
+        regs.update(new)
+        out += regs[0]
+        regs[0] = b""
+        q = q2
+        i += k
+    if q not in sst.final:
+        return False, bytes(out), i
+    for a in sst.final[q]:
+        out += regs[a[1]] if a[0] == "v" else bytes(a[1])
+    return True, bytes(out), i

@@ -26,17 +26,25 @@ CRT = "/root/reference/crt/crt.c"
 REF_DIR = os.path.join(HERE, "_ref")
 
 
-def build_one(kex_path, opt=3, out_dir=REF_DIR, name=None, keep_c=False, act=False):
-    from kleenexlang_b200.frontend.driver import build_ssts, build_oracle_action_pipeline
+def build_one(kex_path, opt=3, out_dir=REF_DIR, name=None, keep_c=False, act=False, la=False):
+    """Variants: <prog> (--act=false --la=false), <prog>.la (--act=false --la=true),
+    <prog>.act (--act=true --la=false --sb=false), <prog>.default (--act=true --la=true
+    --sb=false: the reference's default flags except for the bit suppression)."""
+    from kleenexlang_b200.frontend.driver import build_ssts, build_oracle_action_pipeline, build_lookahead_ssts
     from kleenexlang_b200.frontend.il import compile_sst
     from oracle.emit_c import render_c
     src = open(kex_path, encoding="utf-8").read()
-    ssts = build_oracle_action_pipeline(src, opt) if act else build_ssts(src, opt)
+    if act:
+        ssts = build_oracle_action_pipeline(src, opt, lookahead=la)
+    else:
+        ssts = build_lookahead_ssts(src, opt) if la else build_ssts(src, opt)
     progs = [compile_sst(s) for s in ssts]
-    ctext = render_c(progs, open(CRT).read(), info="%s --opt %d --la=false --act=%s%s" % (
-        os.path.basename(kex_path), opt, "true" if act else "false", " --sb=false" if act else ""))
+    ctext = render_c(progs, open(CRT).read(), info="%s --opt %d --la=%s --act=%s%s" % (
+        os.path.basename(kex_path), opt, "true" if la else "false", "true" if act else "false",
+        " --sb=false" if act else ""))
     os.makedirs(out_dir, exist_ok=True)
-    name = name or os.path.splitext(os.path.basename(kex_path))[0] + (".act" if act else "")
+    suffix = {(False, False): "", (False, True): ".la", (True, False): ".act", (True, True): ".default"}[(act, la)]
+    name = name or os.path.splitext(os.path.basename(kex_path))[0] + suffix
     out = os.path.join(out_dir, name)
     if keep_c:
         open(out + ".c", "w").write(ctext)
@@ -76,11 +84,13 @@ def main(argv):
         if act is None or not act:
             print("built", build_one(p, opt))
         if act is None or act:
-            # the default-mode binary as well (programs with register actions only exist in this mode)
-            try:
-                print("built", build_one(p, opt, act=True))
-            except (ValueError, AssertionError, NotImplementedError) as e:
-                print("skipped %s --act=true: %s" % (os.path.basename(p), e))
+            # the default-mode binaries as well (programs with register actions only exist in this mode),
+            # and the lookahead variants
+            for a_, l_ in ((True, False), (False, True), (True, True)):
+                try:
+                    print("built", build_one(p, opt, act=a_, la=l_))
+                except (ValueError, AssertionError, NotImplementedError, MemoryError) as e:
+                    print("skipped %s --act=%s --la=%s: %s" % (os.path.basename(p), a_, l_, e))
     return 0
 
 
