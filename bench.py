@@ -132,8 +132,8 @@ def reference_output(data: bytes):
 
 
 VARIANT_FLAGS = {"": "--act=false --la=false (1 process)", ".la": "--act=false --la=true (1 process)",
-                 ".act": "--act=true --la=false --sb=false (oracle + action program: 2 processes)",
-                 ".default": "--act=true --la=true --sb=false (the reference's default flags but for --sb: 2 processes)"}
+                 ".act": "--act=true --sb=true --la=false (oracle + action program: 2 processes)",
+                 ".default": "--act=true --sb=true --la=true (the reference's default flags: 2 processes)"}
 
 
 def make_reference_inputs(gen_name, sample_bytes, instances):

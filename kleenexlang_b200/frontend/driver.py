@@ -34,14 +34,15 @@ def build_ssts(src: str, opt: int = 3, actions: bool = False):
     return out
 
 
-def build_oracle_action_pipeline(src: str, opt: int = 3, lookahead: bool = False):
+def build_oracle_action_pipeline(src: str, opt: int = 3, lookahead: bool = False, suppress_bits: bool = False):
     """-> [oracle SST, action SST, oracle SST, action SST, ...]: the phases of
     the reference's default `kexc compile` (`--act=true`; two per pipeline
-    stage, C.hs:507-510) with `--sb=false`; `lookahead` = `--la`."""
+    stage, C.hs:507-510); `lookahead` = `--la`, `suppress_bits` = `--sb` (both on
+    by default in the reference, Options.hs:146-167)."""
     from .oracle_action import build_oracle_action_ssts
     out = []
     for t in build_transducers(src):
-        out.extend(build_oracle_action_ssts(t, opt, lookahead))
+        out.extend(build_oracle_action_ssts(t, opt, lookahead, suppress_bits))
     return out
 
 

@@ -10,10 +10,11 @@ Restates
   src/KMC/SymbolicSST/ActionSST.hs:47-129      `actionToSST`, `interp`, `followEps`, `next`
   src/KMC/SymbolicSST.hs:122-136               `composeRegisterUpdate`
   src/KMC/Frontend/Commands.hs:118-157         generateOracleSSTs / generateActionSSTs
+  src/KMC/SymbolicFST/OutputEquivalence.hs     post-dominators, `optOracle`, `optAction` (`--sb`)
 for byte digits (`Word8`, src/KMC/Frontend.hs:117: base 256, so every code is
-one byte as long as a choice or a range set has at most 256 members) and
-`--sb=false` (no suppression of output-equivalent choices,
-OutputEquivalence.hs) in single-symbol mode (`--la=false`).
+one byte as long as a choice or a range set has at most 256 members), with or
+without the suppression of codes for output-equivalent choices (`--sb`,
+default on) and with or without lookahead in the oracle (`--la`).
 
 Used by the oracle side (oracle/build_ref.py --act: the reference's default
 two-process binary as CPU baseline) and by `kexc simulate`; the CUDA path
@@ -66,9 +67,51 @@ def decode_table(p):
     return tuple(members + [0] * (256 - len(members)))
 
 
-def oracle_fst(fst):
+def post_dominators(fst):
+    """postDominators (OutputEquivalence.hs:20-42) on the control-flow graph of the
+    transitions without output: PDom(p) = {p} | intersection of PDom(q) over p --> q.
+    Sets are bit masks over the states in sorted order."""
+    order = sorted(fst.states)
+    bit = {q: 1 << i for i, q in enumerate(order)}
+    full = (1 << len(order)) - 1
+    succs = {}
+    for q in order:
+        ss = [t for y, t in fst.eps.get(q, ()) if not y]
+        ss += [t for _, f, t in fst.sym.get(q, ()) if f != "copy" and f[0] == "const" and not f[1]]
+        succs[q] = ss
+    dom = {q: full for q in order}
+    while True:
+        new = {}
+        for q in order:
+            m = full
+            for t in succs[q]:
+                m &= dom[t]
+            new[q] = bit[q] | (m if succs[q] else 0)
+        if new == dom:
+            return order, bit, dom
+        dom = new
+
+
+def last_post_dominator(fst):
+    """lastPostDominator (OutputEquivalence.hs:44-56): q -> the post-dominator of q
+    that post-dominates every other one, if any."""
+    order, bit, dom = post_dominators(fst)
+    out = {}
+    for s in order:
+        members = [t for t in order if dom[s] & bit[t]]
+        for t in members:
+            if all(t2 == t or t2 == s or (dom[t2] & bit[t]) for t2 in members):
+                out[s] = t
+                break
+    return out
+
+
+def oracle_fst(fst, lpdom=None):
     """`oracle` (OracleMachine.hs:44-61): drop the outputs, write a code for every
-    non-deterministic choice and for every copied byte of a non-singleton set."""
+    non-deterministic choice and for every copied byte of a non-singleton set.
+    With `lpdom` (`--sb`, optOracle, OutputEquivalence.hs:63-67): no code for the
+    choices of a state whose alternatives all rejoin at its last post-dominator
+    without output."""
     sym, eps = {}, {}
     for q, es in fst.sym.items():
         new = []
@@ -83,7 +126,8 @@ def oracle_fst(fst):
             eps[q] = [((), es[0][1])]
         else:
             assert all(not y for y, _ in es), "choice edges carry no output (Transducer.hs:87-91)"
-            eps[q] = [(code_digits(len(es), ix), q2) for ix, (_, q2) in enumerate(es)]
+            silent = lpdom is not None and lpdom.get(q, q) != q
+            eps[q] = [(() if silent else code_digits(len(es), ix), q2) for ix, (_, q2) in enumerate(es)]
     return FST(fst.states, sym, eps, fst.initial)
 
 
@@ -99,8 +143,10 @@ class ActionFST:
         return q == ()
 
 
-def action_fst(fst):
-    """`action` (ActionMachine.hs:109-127)."""
+def action_fst(fst, lpdom=None):
+    """`action` (ActionMachine.hs:109-127).  With `lpdom` (`--sb`, optAction,
+    OutputEquivalence.hs:58-61) every edge leads to the last post-dominator of its
+    target: the silent region the oracle no longer codes is skipped."""
     sym, eps = {}, {}
     for q in fst.states:
         ns, ne = [], []
@@ -120,6 +166,9 @@ def action_fst(fst):
                 code = code_digits(len(es), ix)
                 assert len(code) == 1
                 ns.append((("const", code[0]), ("const", tuple(y)), q2))
+        if lpdom is not None:
+            ns = [(lab, f, lpdom.get(q2, q2)) for lab, f, q2 in ns]
+            ne = [(y, lpdom.get(q2, q2)) for y, q2 in ne]
         if ns:
             sym[q] = ns
         if ne:
@@ -253,13 +302,14 @@ def _state_key(q):
     return tuple(q)
 
 
-def build_oracle_action_ssts(fst, opt=3, lookahead=False):
+def build_oracle_action_ssts(fst, opt=3, lookahead=False, suppress_bits=False):
     """One pipeline stage as the reference's default mode compiles it
     (compileOracleAction, Commands.hs:204-244): (oracle SST, action SST).
     `lookahead` (`--la`) only concerns the oracle (Commands.hs:126: the action
     machine is deterministic and never looks ahead)."""
     from .sst import sst_from_fst, optimize
-    o = optimize(sst_from_fst(oracle_fst(fst), lookahead=lookahead), opt)
-    a = optimize(action_to_sst(action_fst(fst)), opt, persistent=True)
+    lpdom = last_post_dominator(fst) if suppress_bits else None        # `--sb`, Commands.hs:101-110
+    o = optimize(sst_from_fst(oracle_fst(fst, lpdom), lookahead=lookahead), opt)
+    a = optimize(action_to_sst(action_fst(fst, lpdom)), opt, persistent=True)
     a.action = True
     return o, a

@@ -11,7 +11,8 @@ box without it the prebuilt binaries are used as they are.
 With --act the programs are compiled in the reference's default mode
 (`--act=true`: an oracle and an action program per pipeline stage, two
 processes per stage, tables; frontend/oracle_action.py) as
-`oracle/_ref/<program>.act`; `--la=false --sb=false` in both modes.
+`oracle/_ref/<program>.act` (`--la=false`) and `<program>.default` (`--la=true`, the
+reference's default flag set); `<program>.la` is `--act=false --la=true`.
 
 usage: python oracle/build_ref.py [--opt N] [--act] [prog.kex ...]
 """
@@ -28,20 +29,20 @@ REF_DIR = os.path.join(HERE, "_ref")
 
 def build_one(kex_path, opt=3, out_dir=REF_DIR, name=None, keep_c=False, act=False, la=False):
     """Variants: <prog> (--act=false --la=false), <prog>.la (--act=false --la=true),
-    <prog>.act (--act=true --la=false --sb=false), <prog>.default (--act=true --la=true
-    --sb=false: the reference's default flags except for the bit suppression)."""
+    <prog>.act (--act=true --sb=true --la=false), <prog>.default (--act=true --sb=true
+    --la=true: the reference's default flags, Options.hs:146-167)."""
     from kleenexlang_b200.frontend.driver import build_ssts, build_oracle_action_pipeline, build_lookahead_ssts
     from kleenexlang_b200.frontend.il import compile_sst
     from oracle.emit_c import render_c
     src = open(kex_path, encoding="utf-8").read()
     if act:
-        ssts = build_oracle_action_pipeline(src, opt, lookahead=la)
+        ssts = build_oracle_action_pipeline(src, opt, lookahead=la, suppress_bits=True)
     else:
         ssts = build_lookahead_ssts(src, opt) if la else build_ssts(src, opt)
     progs = [compile_sst(s) for s in ssts]
     ctext = render_c(progs, open(CRT).read(), info="%s --opt %d --la=%s --act=%s%s" % (
         os.path.basename(kex_path), opt, "true" if la else "false", "true" if act else "false",
-        " --sb=false" if act else ""))
+        " --sb=true" if act else ""))
     os.makedirs(out_dir, exist_ok=True)
     suffix = {(False, False): "", (False, True): ".la", (True, False): ".act", (True, True): ".default"}[(act, la)]
     name = name or os.path.splitext(os.path.basename(kex_path))[0] + suffix

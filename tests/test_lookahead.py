@@ -34,8 +34,9 @@ def test_lookahead_golden(v, opt):
 
 @pytest.mark.parametrize("v", load_vectors()[::3], ids=[v["name"] for v in load_vectors()[::3]])
 def test_default_flags_golden(v):
-    """--act=true --la=true (--sb=false): oracle with lookahead + action program."""
-    out = simulate_sst(build_oracle_action_pipeline(v["program"], 3, lookahead=True), v["input"])
+    """--act=true --la=true --sb=true, the reference's default flags: oracle with
+    lookahead and suppressed codes + action program."""
+    out = simulate_sst(build_oracle_action_pipeline(v["program"], 3, lookahead=True, suppress_bits=True), v["input"])
     assert out is not None and vec_matches(v, out)
 
 

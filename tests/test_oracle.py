@@ -89,6 +89,20 @@ def test_oracle_vs_reference_binary_apache():
 ALL_VECS = load_vectors()
 
 
+@pytest.mark.parametrize("v", ALL_VECS, ids=[v["name"] for v in ALL_VECS])
+def test_suppressed_bits_golden(v):
+    """`--sb=true` (OutputEquivalence.hs): no code for a choice whose arms rejoin
+    without output; the action program skips to the last post-dominator.  Same
+    transduction, never a longer code stream."""
+    from kleenexlang_b200.frontend.driver import build_oracle_action_pipeline
+    from kleenexlang_b200.frontend.sst import run_sst
+    plain = build_oracle_action_pipeline(v["program"], 3)
+    sb = build_oracle_action_pipeline(v["program"], 3, suppress_bits=True)
+    st, out, _ = oracle_run(sb, v["input"])
+    assert st == 0 and vec_matches(v, out)
+    assert len(run_sst(sb[0], v["input"])[1]) <= len(run_sst(plain[0], v["input"])[1])
+
+
 @pytest.mark.parametrize("opt", [0, 3])
 @pytest.mark.parametrize("v", ALL_VECS, ids=[v["name"] for v in ALL_VECS])
 def test_oracle_action_pipeline_golden(v, opt):
@@ -130,7 +144,7 @@ def test_default_mode_reference_binary(prog, gen):
     data = workloads.GENERATORS[gen](300000, seed=12).tobytes()
     rc, out, _ = _ref(prog + ".act", data)
     assert (rc, out) == _ref(prog, data)[:2] == oracle_run(build_ssts(src), data)[:2]
-    assert oracle_run(build_oracle_action_pipeline(src), data)[:2] == (0, out)
+    assert oracle_run(build_oracle_action_pipeline(src, suppress_bits=True), data)[:2] == (0, out)
     bad = data[:150001] + b"\x01" + data[150001:]
     st, _, cnt = oracle_run(build_ssts(src), bad)
     rc, _, err = _ref(prog + ".act", bad)
