@@ -46,6 +46,35 @@ def build_oracle_action_pipeline(src: str, opt: int = 3, lookahead: bool = False
     return out
 
 
+def build_regex_transducer(re_src: str):
+    """The regular-expression flavour (`.re` files / `--re`, Commands.hs:68-79):
+    `desugarRegex` (Desugaring.hs:231-239) = the regex as a one-stage program
+    whose reads are copied."""
+    from .regex import parse_regex
+    pl, rdecls = desugar(["main"], [("main", ("re", parse_regex(re_src.rstrip("\n"))))])
+    return construct_transducer(rdecls, pl[0])
+
+
+def build_coder_ssts(re_src: str, opt: int = 3, lookahead: bool = False, suppress_bits: bool = False):
+    """`compileCoder` (Commands.hs:246-275): for a regular expression only the
+    oracle program is compiled -- it writes the bit-coded parse of the input
+    (one code byte per choice and per byte of a non-singleton class)."""
+    from .oracle_action import oracle_fst, last_post_dominator
+    t = build_regex_transducer(re_src)
+    lpdom = last_post_dominator(t) if suppress_bits else None
+    return [optimize(sst_from_fst(oracle_fst(t, lpdom), lookahead=lookahead), opt)]
+
+
+def decode_parse(re_src: str, code: bytes, suppress_bits: bool = False):
+    """Inverse of the coder: the action machine of the same transducer turns the
+    code back into the matched string (ActionMachine.hs:109-127)."""
+    from .oracle_action import action_fst, action_to_sst, last_post_dominator
+    t = build_regex_transducer(re_src)
+    lpdom = last_post_dominator(t) if suppress_bits else None
+    ok, out, _ = run_sst(action_to_sst(action_fst(t, lpdom)), code)
+    return out if ok else None
+
+
 def build_lookahead_ssts(src: str, opt: int = 3):
     """`kexc compile --act=false --la=true`: direct SSTs whose transitions may
     test several symbols (longest deterministic prefixes, SymbolicFST.hs:262-312)."""

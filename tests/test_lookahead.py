@@ -96,3 +96,47 @@ def test_reference_binary_variants(prog):
     assert r.returncode == (0 if ok else 1)
     if not ok:
         assert r.stderr == b"Match error at input symbol %d!\n" % cnt
+
+
+# ---- the regular-expression flavour (.re): bit-coded parses (compileCoder, Commands.hs:246-275)
+RE_CASES = [("(a|b)*c[0-9]+", [b"abbac2016", b"c7", b"bbbbc00"], [b"abx", b"c", b""]),
+            # the regex flavour's {n,m} desugars to n copies + m optional ones (Desugaring.hs:110-115): up to n+m
+            ("(?:ab|a)(?:bc|c)?x{2,3}", [b"abxx", b"abcxxx", b"acxx", b"abxxxxx"], [b"abx", b"abcxxxxxx"]),
+            ("[a-z]+(,[a-z]+)*\\n", [b"ab,c,def\n", b"q\n"], [b"ab,,c\n", b"ab"])]
+
+
+@pytest.mark.parametrize("re_src,good,bad", RE_CASES)
+@pytest.mark.parametrize("sb", [False, True])
+@pytest.mark.parametrize("la", [False, True])
+def test_regex_coder_round_trip(re_src, good, bad, sb, la):
+    """For a regular expression the compiler emits the oracle alone: its output
+    is the bit-coded parse (bytes here: Word8 digits).  Decoding it with the
+    action machine of the same transducer gives the input back; codes follow
+    Coding.hs (fixed width, big-endian, one byte for up to 256 alternatives)."""
+    from kleenexlang_b200.frontend.driver import build_coder_ssts, decode_parse
+    from oracle.sstbin import oracle_run
+    coder = build_coder_ssts(re_src, 3, lookahead=la, suppress_bits=sb)
+    for d in good:
+        ok, code, _ = run_sst(coder[0], d)
+        assert ok and decode_parse(re_src, code, suppress_bits=sb) == d
+        if not la:
+            assert oracle_run(coder, d)[:2] == (0, code)        # the C oracle has no lookahead
+    for d in bad:
+        assert not run_sst(coder[0], d)[0]
+
+
+@needs_crt
+def test_regex_coder_binary(tmp_path):
+    """The emitted C of a coder (one phase, tables for the classes) over crt.c."""
+    from kleenexlang_b200.frontend.driver import build_coder_ssts
+    re_src = "(a|b)*c[0-9]+"
+    for la in (False, True):
+        coder = build_coder_ssts(re_src, 3, lookahead=la, suppress_bits=True)
+        ctext = render_c([compile_sst(s) for s in coder], open(build_ref.CRT).read(), info="coder")
+        exe = str(tmp_path / ("coder%d" % la))
+        r = subprocess.run(["cc", "-O3", "-xc", "-o", exe, "-D FLAG_WORDALIGNED", "-w", "-"], input=ctext.encode(), capture_output=True)
+        assert r.returncode == 0, r.stderr
+        out = subprocess.run([exe], input=b"abbac2016", capture_output=True)
+        assert out.returncode == 0 and out.stdout == run_sst(coder[0], b"abbac2016")[1]
+        assert "tbl1[" in ctext
+        assert subprocess.run([exe], input=b"abx", capture_output=True).returncode == 1
