@@ -22,6 +22,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    import ctypes
+    ctypes.CDLL(LIB)            # unresolved symbols show here, not on the GPU box
     return LIB
 
 

@@ -37,6 +37,7 @@
 #pragma once
 
 #define V4_RECCAP 192u
+#define V4_TAIL_TILES 256u       // tail evaluation (kexcuda.cu run_phase): tiles at the end of the input with exact live sets
 #define V4_MAX_TPL 64u
 #define V4_GB_T 0x80u
 #define V4_GB_C 0x40u
@@ -292,7 +293,7 @@ template <bool REGS, int LOG>
 __global__ void __launch_bounds__(KEX_V4_THREADS, 1)
 k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n_eff, uint32_t ntiles,
         const uint16_t *__restrict__ samples, const uint16_t *__restrict__ blockpre,
-        const uint16_t *__restrict__ chunk_start, const uint8_t *__restrict__ lam_end,
+        const uint16_t *__restrict__ chunk_start, const uint8_t *__restrict__ lam_end, uint32_t tail_first,
         unsigned long long *__restrict__ desc, FastCtl *__restrict__ ctl, uint8_t *__restrict__ out, size_t out_cap,
         unsigned long long out_off, uint32_t stage_bytes, uint32_t warp_bytes, uint32_t reccap, uint32_t force_exact) {
   constexpr uint32_t STRIDE = 1u << LOG;
@@ -392,7 +393,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
         idx -= 256;
       }
       if (lane == 0) {
-        if (!ok) atomicExch(&ctl->error, 1u);
+        if (!ok) atomicCAS(&ctl->error, 0u, 1u);
         st_desc(desc + grp, EF_FLAG_INC | (gex + gsum));
         if (grp == ngroups - 1) ctl->total_out = gex + gsum;
       }
@@ -403,6 +404,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     return;
   }
 
+  if ((force_exact & 64u) && blockIdx.x == 0 && tid == 0) atomicExch(&ctl->error, 2u);   // tests: a broken induction
   // ================================================================= workers
   uint32_t prev_total = 0xFFFFFFFFu;                  // tile whose staging window has not left yet
   uint32_t max_recs = 0, slow_tiles = 0;
@@ -437,12 +439,15 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
         sB = __ldg(F.applyF + (size_t)(smp >> 16) * Q1 + sblk);
       }
     }
-    const uint32_t lam_tile = (REGS && active) ? lam_end[tile] : 0u;
+    // exact live set at the tile's end: known for the tiles of the tail only (tail_first = 0: for all)
+    const bool has_lam = REGS && active && tile >= tail_first;
+    uint32_t lam_tile = has_lam ? lam_end[tile] : 0u;
 
     // ---- forward walk over the G-mode table: emission halves of the entries, lengths, template counts
     uint32_t pr[16];
     uint32_t cntA = 0, cntB = 0, nrA = 0, nrB = 0;
     bool gmode = full && !(force_exact & 1u);
+    uint32_t EB_end = fail_row;
     if (gmode) {
       uint32_t EA = trans_abs + sA * row_bytes + slot4, EB = trans_abs + sB * row_bytes + slot4;
 #pragma unroll
@@ -465,12 +470,17 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       // exact end live set must be the one the table was built for
       bool bad = ((EA & 0xFFFFu) == fail_row) || ((EB & 0xFFFFu) == fail_row) ||
                  ((EA & 0xFFFFu) != trans_abs + sB * row_bytes + slot4);
-      if (REGS && lane == 31u) bad = bad || (lds_u32((EB & 0xFFFFu) + (C << LOG)) != lam_tile);
+      if (has_lam && lane == 31u) bad = bad || (lds_u32((EB & 0xFFFFu) + (C << LOG)) != lam_tile);
       gmode = !__any_sync(0xFFFFFFFFu, bad);
+      EB_end = EB;
     }
     V4Slow sl;
     sl.lam_end = 0;
     if (!gmode) {
+      // tail evaluation: a tile without exact live sets that is not G-consistent, or the anchor tile
+      // (the first one of the tail) itself: the induction has no base -- the host repeats the phase
+      // with exact live sets for every tile
+      if (REGS && active && tail_first && tile <= tail_first && lane == 0) atomicExch(&ctl->error, 2u);
       // exact evaluation from the tables in global memory (rare)
       sl = v4_slow_count(P, F, in + tbase + lo, cnt_pos, sA, lam_tile, lane);
       cntA = sl.cnt; cntB = 0; nrA = sl.nrec; nrB = 0;
@@ -502,7 +512,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
         asm volatile("prefetch.global.L2 [%0];" ::"l"(in + nt * V3_TILE + lane * 32u));
         if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(samples + nt * V3_SPT + lane * 16u));
         if (lane == 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blockpre + nt * (V3_TILE / V3_BLK)));
-        if (REGS && lane == 5u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lam_end + nt));
+        if (REGS && lane == 5u && nt >= tail_first) asm volatile("prefetch.global.L2 [%0];" ::"l"(lam_end + nt));
       }
     }
     __threadfence_block();
@@ -556,7 +566,12 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
         if (lane == 0) atomicExch(&ctl->overflow, 1u);
         continue;
       }
-      if (gmode) sl = v4_slow_count(P, F, in + tbase + lo, cnt_pos, sA, lam_tile, lane);
+      if (gmode) {
+        // before the tail the live set at the end of a G-consistent tile is G[end state] (by induction
+        // from the anchor tile; the host repeats the run exactly if that induction breaks anywhere)
+        if (REGS && !has_lam) lam_tile = __shfl_sync(0xFFFFFFFFu, lds_u32((EB_end & 0xFFFFu) + (C << LOG)), 31);
+        sl = v4_slow_count(P, F, in + tbase + lo, cnt_pos, sA, lam_tile, lane);
+      }
       v4_slow_write(P, F, in + tbase + lo, cnt_pos, sA, sl.lam_end, o_end, 0u, out + gbase);
       __syncwarp();
     }

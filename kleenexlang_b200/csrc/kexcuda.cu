@@ -668,6 +668,7 @@ struct PhaseHost {
   std::vector<uint32_t> h_trans2, h_BE, g_static_tab;   // host copies for learn_gmode
   std::vector<uint8_t> g_static;      // [Q+1] the blob's static choice of G
   bool v4_learned = false, v4_off = false;
+  bool v4_tail_ok = true;             // tail evaluation has not had to be repeated exactly so far
   uint32_t v4_relearns = 0, v4_last_exact = 0;
   uint32_t v4_stage = 3072, v4_reccap = V4_RECCAP;
   // action-interpreter phase (kex_act.cuh): no SST tables at all
@@ -702,6 +703,8 @@ struct Ctx {
   size_t lvl_count[8];
   int nlevels = 0;
   uint32_t sh_phase = 0;
+  // G-mode tail evaluation (run_phase): exact live sets exist only for tiles >= tail_first; 0 = for all
+  size_t tail_first = 0;
 };
 
 struct kex_program {
@@ -730,6 +733,8 @@ struct kex_program {
   size_t emit_out_off = 0;            // v3 emit: offset of this shard's output inside d_out
   uint32_t only_phase = 0;            // 1-based phase selected by kex_select_phase, 0 = all
 };
+
+#define KEX_NEED_EXACT 100     // internal: repeat the phase with exact live sets for every tile
 
 #define CK(call)                                                              \
   do {                                                                        \
@@ -1406,7 +1411,7 @@ extern "C" const char *kex_strerror(int code) {
 
 // ---------------------------------------------------------------- shard steps
 static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, cudaStream_t st);
-static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st);
+static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st, size_t tail_first = 0);
 static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t *d_out, size_t out_cap, size_t *out_len,
                         cudaStream_t st);
 
@@ -1633,12 +1638,13 @@ static int do_summarize_fast(kex_program *p, uint32_t phase, const uint8_t *d_in
   return KEX_OK;
 }
 
-static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st) {
+static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st, size_t tail_first) {
   PhaseHost &ph = p->phases[p->c->sh_phase];
   const PhaseDev &P = ph.dev;
   const uint32_t Q1 = P.Q + 1, NL = ph.fdev.NL;
   const size_t nchunks = p->c->sh_nchunks, n = p->c->sh_n;
   const int top = p->c->nlevels - 1;
+  p->c->tail_first = tail_first;
   k_set_u16<<<1, 1, 0, st>>>((uint16_t *)p->c->starts[top].p, start_state);
   p->launches++;
   for (int l = top; l >= 1; --l) {
@@ -1650,13 +1656,17 @@ static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st) {
   }
   int rc;
   if (ph.v3.ok) {
-    const size_t ntiles = (n + V3_TILE - 1) / V3_TILE;
+    const size_t ntiles_all = (n + V3_TILE - 1) / V3_TILE;
+    // tail evaluation: only the tiles from tail_first on (a chunk boundary) are walked; a failure
+    // anywhere before shows as the FAIL state at their start (it is absorbing)
+    const size_t t0 = tail_first, ntiles = ntiles_all - t0;
     if ((rc = ensure(p, p->c->bmaps[0], ntiles * NL))) return rc;
     CK(cudaMemsetAsync(p->c->res_dev.p, 0xFF, sizeof(unsigned long long), st));     // fail_pos = none
     if (p->timing) CK(cudaEventRecord(p->ev[2], st));
     k3_seams<<<(unsigned)((ntiles + 255) / 256), 256, ph.smem_seams3, st>>>(
-        P, ph.fdev, p->c->sh_in, n, ntiles, (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p,
-        (const uint16_t *)p->c->maps[0].p, (uint8_t *)p->c->bmaps[0].p, (RunResult *)p->c->res_dev.p);
+        P, ph.fdev, p->c->sh_in + t0 * V3_TILE, n - t0 * V3_TILE, ntiles,
+        (const uint16_t *)p->c->blockpre.p + t0 * (V3_TILE / V3_BLK), (const uint16_t *)p->c->starts[0].p + t0 / V3_TPC,
+        (const uint16_t *)p->c->maps[0].p + (t0 / V3_TPC) * Q1, (uint8_t *)p->c->bmaps[0].p, (RunResult *)p->c->res_dev.p);
     p->launches++;
     if (p->timing) CK(cudaEventRecord(p->ev[3], st));
   } else {
@@ -1700,9 +1710,12 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
   int rc;
   size_t cnt[8];
   int nl = 0;
-  level_counts(ntiles, cnt, &nl);
+  // tail evaluation: bmaps / lams hold the tiles [tail_first, ntiles) only (run_phase never shortens
+  // n_eff in that mode)
+  const size_t tail_first = p->c->tail_first;
+  level_counts(ntiles - tail_first, cnt, &nl);
   if (NL > 1) {
-    if ((rc = lam_up(p, ntiles, cnt, &nl, st))) return rc;
+    if ((rc = lam_up(p, ntiles - tail_first, cnt, &nl, st))) return rc;
     for (int l = 0; l < nl; ++l) if ((rc = ensure(p, p->c->lams[l], cnt[l]))) return rc;
     k_set_u8<<<1, 1, 0, st>>>((uint8_t *)p->c->lams[nl - 1].p, lam_end);
     p->launches++;
@@ -1727,6 +1740,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     if (const char *e = getenv("KEX_V4_RECCAP")) { const long x = atol(e); if (x >= 8) ph.v4_reccap = (uint32_t)x; }
     uint32_t force_exact = getenv("KEX_V4_EXACT") ? 1u : 0u;
     if (const char *e = getenv("KEX_V4_KNOCK")) force_exact |= (uint32_t)atoi(e) & ~1u;     // timing experiments only (wrong output)
+    if (tail_first && getenv("KEX_V4_TAIL_TEST")) force_exact |= 64u;                       // tests: pretend tile 0 broke the induction
     const uint32_t warp_bytes = (ph.v4_stage + 128u + ph.v4_reccap * 8u + 127u) & ~127u;
     uint32_t nwork = (uint32_t)(((size_t)V3_SMEM_MAX - V.o_warp) / warp_bytes);
     if (nwork > 31u) nwork = 31u;
@@ -1750,7 +1764,8 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     if (regs == R && V.log == L)                                                                                     \
       k4_emit<R, L><<<(unsigned)ctas, nwarp * 32u, smem4, st>>>(                                                     \
           P, ph.fdev, V, p->c->sh_in, n_eff, (uint32_t)ntiles, (const uint16_t *)p->c->samples.p,                   \
-          (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p, (const uint8_t *)p->c->lams[0].p,  \
+          (const uint16_t *)p->c->blockpre.p, (const uint16_t *)p->c->starts[0].p,                                  \
+          (const uint8_t *)p->c->lams[0].p - tail_first, (uint32_t)tail_first,                                      \
           (unsigned long long *)p->c->desc.p, (FastCtl *)p->c->ctl.p, d_out, out_cap,                                \
           (unsigned long long)p->emit_out_off, ph.v4_stage, warp_bytes, ph.v4_reccap, force_exact);
     V4_EACH(V4_LAUNCH)
@@ -1760,7 +1775,8 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     if (p->timing) CK(cudaEventRecord(p->ev[5], st));
     CK(cudaGetLastError());
     if ((rc = fetch_sync(p, p->c->ctl_host, p->c->ctl.p, sizeof(FastCtl), st))) return rc;
-    if (p->c->ctl_host->error) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
+    if (p->c->ctl_host->error == 1u) { p->cuda_err = "emit: chained scan timed out"; return KEX_ERR_CUDA; }
+    if (p->c->ctl_host->error == 2u) return KEX_NEED_EXACT;      // tail evaluation: a tile before the tail needs exact live sets
     const size_t total = (size_t)p->c->ctl_host->total_out;
     *out_len = total;
     if (p->c->ctl_host->overflow || total + p->emit_out_off > out_cap) return KEX_ERR_OUT_CAP;
@@ -1789,6 +1805,7 @@ static int do_emit_fast(kex_program *p, uint32_t lam_end, size_t n_eff, uint8_t 
     if (want > ph.v4_stage || want + 1024u < ph.v4_stage) ph.v4_stage = want;
     return KEX_OK;
   }
+  if (tail_first) return KEX_ERR_ARG;              // only the G-mode kernel evaluates tails
   if (ph.v3.ok) {
     // one CTA per SM: up to 31 worker warps + 1 scan warp (as many workers as the
     // staging windows leave room for); every CTA must be resident because groups
@@ -2078,10 +2095,26 @@ static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t
   uint32_t end_state = P.init;
   size_t n_eff = n;
   bool failed = false;
+  // G-mode tail evaluation (kex_v4.cuh): once G is learnt, the live set at every position of a
+  // G-consistent run is G[state] -- by induction backwards from any tile boundary where the exact
+  // live set equals G[state].  So k3_seams and the live-set tree only run over the last
+  // V4_TAIL_TILES tiles (where the end of the input makes the live sets differ from G); the first
+  // tail tile is the anchor: it must verify in G-mode.  Failures show as the FAIL state at the
+  // tail's start.  Anything unexpected (a failure, an inconsistent tile before the tail) repeats
+  // the phase with exact live sets everywhere and switches the shortcut off for this program.
+  const size_t ntiles_all = (n + V3_TILE - 1) / V3_TILE;
+  size_t tail_first = 0;
+  if (ph.v4.ok && !ph.v4_off && ph.v4_learned && ph.v4_tail_ok && ntiles_all >= 4 * V4_TAIL_TILES && !getenv("KEX_V4_NOTAIL") &&
+      !getenv("KEX_V4_EXACT"))
+    tail_first = (ntiles_all - V4_TAIL_TILES) / V3_TPC * V3_TPC;
   if (n > 0) {
     int rc = do_summarize(p, phase, d_in, n, st);
     if (rc) return rc;
-    if ((rc = do_walk(p, P.init, st))) return rc;
+    if (tail_first) {
+      if ((rc = do_walk_fast(p, P.init, st, tail_first))) return rc;
+      if (p->c->res_host->fail_pos != KEX_NONE64 || p->c->res_host->end_state == P.Q) tail_first = 0;   // a failure: exact path
+    }
+    if (!tail_first && (rc = do_walk(p, P.init, st))) return rc;
     const unsigned long long f = p->c->res_host->fail_pos;
     if (f != KEX_NONE64) { failed = true; n_eff = (size_t)f; }
     end_state = p->c->res_host->end_state;
@@ -2093,6 +2126,12 @@ static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t
   const uint32_t live = accept ? final_code(ph, end_state) : 0u;
   size_t body = 0;
   int rc = do_emit(p, live, n_eff, d_out, out_cap, &body, st);
+  if (rc == KEX_NEED_EXACT) {
+    ph.v4_tail_ok = false;
+    if (getenv("KEX_DEBUG")) fprintf(stderr, "kexcuda: v4: tail evaluation met a tile that needs exact live sets -> exact run\n");
+    if ((rc = do_walk(p, P.init, st))) return rc;
+    rc = do_emit(p, live, n_eff, d_out, out_cap, &body, st);
+  }
   if (rc == KEX_ERR_OUT_CAP) { *out_len = body + (accept ? ph.acts[fa].total_len : 0); return rc; }
   if (rc) return rc;
   if (accept) {

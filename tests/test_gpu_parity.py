@@ -285,7 +285,7 @@ V4_PROGS = ["csv2json", "fastq2fasta"]      # iso_datetime: 37 x 14 entries do n
 
 @pytest.mark.parametrize("name", PROGS)
 @pytest.mark.parametrize("knob", [{}, {"KEX_V4_EXACT": "1"}, {"KEX_V4_STAGE": "256", "KEX_V4_RECCAP": "8"}, {"KEX_NO_V4": "1"},
-                                  {"KEX_V3_WORKERS": "3"}, {"KEX_V4_LOG6": "1"}])
+                                  {"KEX_V3_WORKERS": "3"}, {"KEX_V4_LOG6": "1"}, {"KEX_V4_NOTAIL": "1"}, {"KEX_V4_TAIL_TEST": "1"}])
 def test_v4_paths_forced(name, knob, monkeypatch):
     """The G-mode emit kernel (kex_v4.cuh) and its rarely taken paths, forced:
     every tile evaluated exactly from the tables in global memory
@@ -294,7 +294,10 @@ def test_v4_paths_forced(name, knob, monkeypatch):
     CTA (many groups per CTA: the chained scan and the deferred stage-out).
     Inputs long enough for G to be learnt from the run itself (>= 2 chunk
     boundaries), twice (the second run uses the learnt table and the window
-    sized from the first), truncated, and rejecting."""
+    sized from the first -- and, from then on, the tail evaluation: k3_seams and
+    the live-set tree over the last 256 tiles only; KEX_V4_NOTAIL keeps them
+    over everything, KEX_V4_TAIL_TEST makes the kernel report a broken induction
+    so that the host repeats the run exactly), truncated, and rejecting."""
     from kleenexlang_b200.runtime import CompiledProgram
     for k, v in knob.items():
         monkeypatch.setenv(k, v)
