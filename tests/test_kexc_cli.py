@@ -174,3 +174,20 @@ def test_malformed_programs_exit_with_a_message(tmp_path):
         r = subprocess.run(KEXC + ["compile", str(src), "--out", str(tmp_path / "o"), "--quiet"], capture_output=True,
                            cwd=ROOT, env=ENV)
         assert r.returncode == 1 and msg in r.stderr and b"Traceback" not in r.stderr
+
+
+def test_simulate_default_flags_and_regex_flavour(tmp_path):
+    """`simulate --sim=sst` with the reference's default flags runs the oracle +
+    action SSTs (tables, lookahead, suppressed bits) on the CPU; a `.re` file is
+    the regular-expression flavour: the bit-coded parse."""
+    prog = os.path.join(PROGRAMS, "add-commas.kex")
+    for flags in (["--sim=sst"], ["--sim=sst", "--la=false"], ["--sim=sst", "--act=false"], ["--sim=sst", "--act=false", "--la=false"],
+                  ["--sim=sst", "--sb=false"]):
+        r = subprocess.run(KEXC + ["simulate", prog, "--quiet", *flags], input=b"1234567\n", capture_output=True, cwd=ROOT, env=ENV)
+        assert (r.returncode, r.stdout) == (0, b"1,234,567\n"), flags
+    re_file = tmp_path / "t.re"
+    re_file.write_text("(a|b)*c\n")
+    r = subprocess.run(KEXC + ["simulate", str(re_file), "--quiet", "--sb=false"], input=b"abc", capture_output=True, cwd=ROOT, env=ENV)
+    assert (r.returncode, r.stdout) == (0, bytes([0, 0, 0, 1, 1]))       # iterate, a, iterate, b, leave
+    r = subprocess.run(KEXC + ["simulate", str(re_file), "--quiet"], input=b"abx", capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 1
