@@ -377,6 +377,14 @@ k3_seams(PhaseDev P, FastDev F, const uint8_t *__restrict__ in, size_t n, size_t
 }
 
 // ------------------------------------------------------------------ k3_emit
+// Workers wait for the scan warp's offsets on a named barrier from three places (deferred stage-out,
+// window exceeded, after the loop).  PTX only asks for warp-level convergence at a `bar.sync`, but
+// compute-sanitizer's synccheck reports warps of one block meeting the same barrier at different
+// program counters; through this out-of-line function they all meet it at one.
+__device__ __noinline__ void ef_wait_bases(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 extern __shared__ __align__(1024) uint8_t smem_v3[];
 
 // Staging windows are addressed through this swizzle: address bits 7-11 (the
@@ -807,7 +815,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
     // ---- the previous tile leaves its staging window only now: its global offset
     // had this tile's load, forward walk and count pass to arrive
     if (prev_total != 0xFFFFFFFFu) {
-      asm volatile("bar.sync %0, %1;" ::"r"(3u + (par ^ 1u)), "r"(bar_n) : "memory");
+      ef_wait_bases(3u + (par ^ 1u), bar_n);
       const unsigned long long gb = bases[(par ^ 1u) * 32u + warp];
       if (gb + prev_total > (unsigned long long)out_cap) {
         if (lane == 0) atomicExch(&ctl->overflow, 1u);
@@ -840,7 +848,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       // ---- the tile's output exceeds the staging window: byte stores to global.
       // Input words and action ids are parked in the (idle) staging window so
       // that the loop can stay rolled.
-      asm volatile("bar.sync %0, %1;" ::"r"(3u + par), "r"(bar_n) : "memory");
+      ef_wait_bases(3u + par, bar_n);
       const unsigned long long gbase = bases[par * 32u + warp];
       if (gbase + total > (unsigned long long)out_cap) {
         if (lane == 0) atomicExch(&ctl->overflow, 1u);
@@ -871,7 +879,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
   if (lane == 0 && max_recs) atomicMax(&ctl->pad, max_recs);
   if (prev_total != 0xFFFFFFFFu) {
     // the last tile of this warp (par has advanced past its round)
-    asm volatile("bar.sync %0, %1;" ::"r"(3u + (par ^ 1u)), "r"(bar_n) : "memory");
+    ef_wait_bases(3u + (par ^ 1u), bar_n);
     const unsigned long long gb = bases[(par ^ 1u) * 32u + warp];
     if (gb + prev_total > (unsigned long long)out_cap) {
       if (lane == 0) atomicExch(&ctl->overflow, 1u);

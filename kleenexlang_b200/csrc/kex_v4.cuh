@@ -519,7 +519,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     asm volatile("bar.arrive %0, %1;" ::"r"(1u + par), "r"(bar_n) : "memory");
     // ---- the previous tile leaves its staging window only now
     if (prev_total != 0xFFFFFFFFu) {
-      asm volatile("bar.sync %0, %1;" ::"r"(3u + (par ^ 1u)), "r"(bar_n) : "memory");
+      ef_wait_bases(3u + (par ^ 1u), bar_n);
       const unsigned long long gb = bases[(par ^ 1u) * 32u + warp];
       if (gb + prev_total > (unsigned long long)out_cap) {
         if (lane == 0) atomicExch(&ctl->overflow, 1u);
@@ -560,7 +560,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       prev_total = total;                                          // staged out after the next tile's forward pass
     } else {
       // ---- the tile's output exceeds the staging window or the record slots: exact path, byte stores to global
-      asm volatile("bar.sync %0, %1;" ::"r"(3u + par), "r"(bar_n) : "memory");
+      ef_wait_bases(3u + par, bar_n);
       const unsigned long long gbase = bases[par * 32u + warp];
       if (gbase + total > (unsigned long long)out_cap) {
         if (lane == 0) atomicExch(&ctl->overflow, 1u);
@@ -579,7 +579,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
   if (lane == 0 && max_recs) atomicMax(&ctl->pad, max_recs);
   if (lane == 0 && slow_tiles) atomicAdd(&ctl->ticket, slow_tiles);     // tiles evaluated exactly (host: is G still right?)
   if (prev_total != 0xFFFFFFFFu) {
-    asm volatile("bar.sync %0, %1;" ::"r"(3u + (par ^ 1u)), "r"(bar_n) : "memory");
+    ef_wait_bases(3u + (par ^ 1u), bar_n);
     const unsigned long long gb = bases[(par ^ 1u) * 32u + warp];
     if (gb + prev_total > (unsigned long long)out_cap) {
       if (lane == 0) atomicExch(&ctl->overflow, 1u);

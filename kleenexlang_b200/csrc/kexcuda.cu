@@ -1661,7 +1661,7 @@ static int do_walk_fast(kex_program *p, uint32_t start_state, cudaStream_t st, s
     // anywhere before shows as the FAIL state at their start (it is absorbing)
     const size_t t0 = tail_first, ntiles = ntiles_all - t0;
     if ((rc = ensure(p, p->c->bmaps[0], ntiles * NL))) return rc;
-    CK(cudaMemsetAsync(p->c->res_dev.p, 0xFF, sizeof(unsigned long long), st));     // fail_pos = none
+    CK(cudaMemsetAsync(p->c->res_dev.p, 0xFF, sizeof(RunResult), st));              // fail_pos = none (and no uninitialised padding reaches k_publish)
     if (p->timing) CK(cudaEventRecord(p->ev[2], st));
     k3_seams<<<(unsigned)((ntiles + 255) / 256), 256, ph.smem_seams3, st>>>(
         P, ph.fdev, p->c->sh_in + t0 * V3_TILE, n - t0 * V3_TILE, ntiles,
