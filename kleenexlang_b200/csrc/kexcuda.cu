@@ -2082,7 +2082,7 @@ static int run_phase_act(kex_program *p, uint32_t phase, const uint8_t *d_in, si
 }
 
 static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
-                     size_t *out_len, int *status, size_t *fail_count, cudaStream_t st) {
+                     size_t *out_len, int *status, size_t *fail_count, cudaStream_t st, bool feeds_interpreter = false) {
   PhaseHost &ph = p->phases[phase];
   if (ph.act) {
     // status and count are the transducer phase's (kex_run_device keeps them)
@@ -2150,7 +2150,10 @@ static int run_phase(kex_program *p, uint32_t phase, const uint8_t *d_in, size_t
     *status = KEX_ACCEPT;
     *fail_count = 0;
   } else {
-    *out_len = body / 16384 * 16384;   // whole 16 KiB flushes only (crt.c:140-159, 217-227)
+    // whole 16 KiB flushes only (crt.c:140-159, 217-227) -- unless this is the transducer phase of a stage
+    // with register actions: its stream is not stdout but the interpreter's input, everything up to the
+    // failing symbol is interpreted and the flush rule applies once, to the stage's output (kex_run_device)
+    *out_len = feeds_interpreter ? body : body / 16384 * 16384;
     *status = KEX_REJECT;
     *fail_count = n_eff;
   }
@@ -2182,14 +2185,15 @@ extern "C" int kex_run_device(kex_program *p, const uint8_t *d_in, size_t n, uin
     }
     size_t ol = 0, fc = 0;
     int stt = 0;
-    int rc = run_phase(p, (uint32_t)i, cur, cur_n, dst, cap, &ol, &stt, &fc, st);
+    const bool feeds = i + 1 < nph && p->phases[i + 1].act;
+    int rc = run_phase(p, (uint32_t)i, cur, cur_n, dst, cap, &ol, &stt, &fc, st, feeds);
     if (rc == KEX_ERR_OUT_CAP && i + 1 < nph) {
       Buf &b = p->inter[i & 1];
       CK(cudaStreamSynchronize(st));
       if ((rc = ensure(p, b, ol + 65536))) return rc;
       dst = (uint8_t *)b.p;
       cap = b.cap;
-      rc = run_phase(p, (uint32_t)i, cur, cur_n, dst, cap, &ol, &stt, &fc, st);
+      rc = run_phase(p, (uint32_t)i, cur, cur_n, dst, cap, &ol, &stt, &fc, st, feeds);
     }
     if (rc) { *out_len = ol; return rc; }
     if (p->phases[i].act && i > first && *status == KEX_REJECT) {

@@ -99,8 +99,25 @@ static void run_atoms(const uint32_t *p, uint32_t n, uint32_t self, int to_strea
 }
 
 /* returns 0 accept, 1 reject, <0 malformed program / output overflow (-3: *outlen = needed) */
+static int oracle_run_impl(const void *sst, size_t sstlen, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                           size_t *outlen, size_t *count, int keep_pending);
+
 int kex_oracle_run(const void *sst, size_t sstlen, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                    size_t *outlen, size_t *count) {
+  return oracle_run_impl(sst, sstlen, in, n, out, cap, outlen, count, 0);
+}
+
+/* The transducer phase of a stage with register actions (frontend/actions.py): its output is not
+ * the program's stdout but the action stream handed to the action interpreter inside the same
+ * stage, so on a reject everything produced up to the failing symbol is handed on; the 16 KiB
+ * flush rule applies once, to the interpreted output (oracle/sstbin.py). */
+int kex_oracle_run_stream(const void *sst, size_t sstlen, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                          size_t *outlen, size_t *count) {
+  return oracle_run_impl(sst, sstlen, in, n, out, cap, outlen, count, 1);
+}
+
+static int oracle_run_impl(const void *sst, size_t sstlen, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                           size_t *outlen, size_t *count, int keep_pending) {
   const uint32_t *p = (const uint32_t *)sst;
   if (sstlen < 16 || p[0] != 0x5453534Bu) return -1;
   const uint32_t nstates = p[1], nvars = p[2], init = p[3];
@@ -167,7 +184,7 @@ int kex_oracle_run(const void *sst, size_t sstlen, const uint8_t *in, size_t n, 
     q = tr->dest;
   }
   *count = i;
-  if (status == 0) {   /* flush_outbuf (crt/crt.c:334-346) */
+  if (status == 0 || keep_pending) {   /* flush_outbuf (crt/crt.c:334-346) */
     if (o->flushed + o->pend <= o->cap) memcpy(o->out + o->flushed, o->win, o->pend);
     else o->overflow = 1;
     o->flushed += o->pend;

@@ -69,13 +69,16 @@ def oracle_run(ssts, data: bytes):
         _lib.kex_oracle_run.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                         ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
                                         ctypes.POINTER(ctypes.c_size_t)]
+        _lib.kex_oracle_run_stream.argtypes = _lib.kex_oracle_run.argtypes
         _lib.kex_oracle_act.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p,
                                         ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     status, count = 0, 0
-    for s in ssts:
+    ssts = list(ssts)
+    for k, s in enumerate(ssts):
         if hasattr(s, "nregs"):
             # action interpreter phase (frontend/actions.py); a stage that rejected in its
-            # transducer phase stays rejected and keeps whole 16 KiB flushes only
+            # transducer phase stays rejected: the stream up to the failing symbol is interpreted
+            # and the result keeps whole 16 KiB flushes only (one truncation, on the stage's output)
             buf = ctypes.create_string_buffer(max(1, len(data)))
             ol = ctypes.c_size_t()
             rc = _lib.kex_oracle_act(data, len(data), s.nregs, buf, len(data), ctypes.byref(ol))
@@ -90,7 +93,9 @@ def oracle_run(ssts, data: bytes):
         while True:
             buf = ctypes.create_string_buffer(cap)
             ol, cnt = ctypes.c_size_t(), ctypes.c_size_t()
-            rc = _lib.kex_oracle_run(blob, len(blob), data, len(data), buf, cap, ctypes.byref(ol), ctypes.byref(cnt))
+            feeds_interpreter = k + 1 < len(ssts) and hasattr(ssts[k + 1], "nregs")
+            run = _lib.kex_oracle_run_stream if feeds_interpreter else _lib.kex_oracle_run
+            rc = run(blob, len(blob), data, len(data), buf, cap, ctypes.byref(ol), ctypes.byref(cnt))
             if rc == -3:
                 cap = ol.value + 4096
                 continue

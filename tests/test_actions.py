@@ -213,3 +213,25 @@ def test_reference_register_programs(v):
             assert oracle_run(phases, v["input"])[:2] == (0, v["output"])
         else:
             assert v["name"] in ("drex_rev-dict", "sort_ab", "worstcase", "dna_regex_noalias_2")
+
+
+def test_reject_inside_an_action_stage_truncates_once():
+    """A stage with register actions that rejects: the action stream produced up
+    to the failing symbol is interpreted in full (the bottom builder is the
+    result) and the 16 KiB flush rule (crt/crt.c:107-159,217-227) applies once,
+    to the stage's output -- not to the intermediate stream as well."""
+    from kleenexlang_b200.frontend.sst import run_sst
+    src = source("swap_fields")
+    ssts = build_ssts(src, 3, actions=True)
+    good = gen("swap_fields", 60000, 7)
+    cut = good.index(b"\n", 50000) + 1
+    bad = good[:cut] + b"a line without the separator\n" + good[cut:]
+    st, out, cnt = oracle_run(ssts, bad)
+    ok, stream, consumed = run_sst(ssts[0], bad)
+    assert st == 1 and not ok and cnt == consumed
+    assert len(stream) > 3 * 16384 and len(stream) % 16384 != 0
+    _, full, _ = oracle_run(ssts[1:], stream)                     # the interpreter alone, nothing truncated
+    assert out == full[:len(full) // 16384 * 16384] and len(out) >= 2 * 16384
+    # truncating the intermediate stream first would have lost more
+    _, twice, _ = oracle_run(ssts[1:], stream[:len(stream) // 16384 * 16384])
+    assert len(twice) // 16384 * 16384 <= len(out)

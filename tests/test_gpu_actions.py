@@ -127,3 +127,17 @@ def test_reference_register_programs_gpu(v):
     got = prog.run(big)
     assert got[0] == est and (est != 0 or got[1] == eout)
     prog.close()
+
+
+def test_reject_inside_an_action_stage_gpu():
+    """Reject of a stage with register actions after several 16 KiB of stream:
+    one truncation, on the stage's output (tests/test_actions.py has the oracle
+    side of this rule)."""
+    prog, ssts = gpu_prog("swap_fields")
+    good = gen("swap_fields", 200000, 7)
+    for at in (50000, 150000):
+        cut = good.index(b"\n", at) + 1
+        bad = good[:cut] + b"a line without the separator\n" + good[cut:]
+        exp = oracle_run(ssts, bad)
+        assert exp[0] == 1 and len(exp[1]) >= 2 * 16384
+        assert prog.run(bad) == exp
