@@ -319,8 +319,8 @@ def equals_periodic(torch, d_out, length, pos, d_ref):
         s = (pos + i) % P
         m = min(P - s, length - i)
         if s == 0 and m == P:
-            k = (length - i) // P                     # whole copies at once (up to 64 per comparison)
-            k = min(k, 64)
+            k = (length - i) // P                     # whole copies at once (the comparison allocates k * P bytes)
+            k = min(k, max(1, (1 << 31) // P))
             if not bool((d_out[i:i + k * P].view(k, P) == d_ref[None, :]).all()):
                 return False
             i += k * P
