@@ -44,6 +44,7 @@ extern "C" {
 #define KEX_ERR_OUT_CAP     -3   /* output buffer too small; *out_len = bytes needed */
 #define KEX_ERR_UNSUPPORTED -4   /* program exceeds a device-table limit          */
 #define KEX_ERR_ARG         -5   /* bad argument (null, misaligned input, phase)  */
+#define KEX_RETRY_EXACT      1   /* kex_shard_emit after kex_set_shard_tail: repeat the shard steps (see there) */
 
 /* Match status, mirroring the exit status of the reference binary
  * (src/KMC/Program/Backends/C.hs:79-81). */
@@ -147,6 +148,17 @@ int kex_stitch_live(const kex_program *p, const uint8_t *seams, size_t nshards,
                     uint32_t final_code, uint32_t *codes);
 int kex_shard_emit(kex_program *p, uint32_t seam_code, size_t n_eff,
                    uint8_t *d_out, size_t out_cap, size_t *out_len, void *stream);
+
+/* Opt-in for the sharded entry points: let kex_shard_walk / kex_shard_emit use the G-mode tail
+ * evaluation (exact live sets only for the last tiles of the shard; programs with state-determined
+ * live sets, after a first evaluation has learnt them).  kex_shard_walk then reports the shard's seam
+ * summary under the assumption that every tile before the tail is consistent with the learnt table;
+ * kex_shard_emit verifies it and returns KEX_RETRY_EXACT (1) if it does not hold.  In that case the
+ * summary this rank gave to the others was not reliable: EVERY rank must repeat kex_shard_walk ->
+ * exchange -> kex_stitch_live -> kex_shard_emit (the failing rank evaluates exactly from then on),
+ * so the callers all-reduce the return code of kex_shard_emit.  Off by default: without it the three
+ * steps never need repeating. */
+int kex_set_shard_tail(kex_program *p, int enabled);
 
 /* Final-state action: is `state` accepting, the seam code of the end-of-input
  * action (which registers it flushes), and its literal tail

@@ -669,6 +669,7 @@ struct PhaseHost {
   std::vector<uint8_t> g_static;      // [Q+1] the blob's static choice of G
   bool v4_learned = false, v4_off = false;
   bool v4_tail_ok = true;             // tail evaluation has not had to be repeated exactly so far
+  std::vector<uint8_t> h_G;           // host copy of the G the device tables were built for
   uint32_t v4_relearns = 0, v4_last_exact = 0;
   uint32_t v4_stage = 3072, v4_reccap = V4_RECCAP;
   // action-interpreter phase (kex_act.cuh): no SST tables at all
@@ -730,6 +731,7 @@ struct kex_program {
   // host pipeline (kex_run_host)
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> pipe_ev;
+  bool shard_tail = false;            // kex_set_shard_tail: kex_shard_walk / kex_shard_emit may use the G-mode tail evaluation
   size_t emit_out_off = 0;            // v3 emit: offset of this shard's output inside d_out
   uint32_t only_phase = 0;            // 1-based phase selected by kex_select_phase, 0 = all
 };
@@ -1076,6 +1078,7 @@ static int learn_gmode(kex_program *p, PhaseHost &ph, size_t ntiles, cudaStream_
   build_gtab(ph, obs, G, gtab);
   int rc = upload_gtab(p, ph, G, gtab, st);
   if (rc) return rc;
+  ph.h_G = G;
   ph.v4_learned = true;
   if (getenv("KEX_DEBUG")) fprintf(stderr, "kexcuda: v4: G learnt from %zu chunk boundaries (%zu distinct pairs)\n", N, order.size());
   return KEX_OK;
@@ -1938,7 +1941,7 @@ extern "C" size_t kex_seam_bytes(const kex_program *p) {
 // position, and the shard's seam summary (how the seam code at its end maps to
 // its start).
 static int shard_walk_seam(kex_program *p, uint32_t start_state, uint32_t *end_state, size_t *fail_pos, uint8_t *h_seam,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool allow_tail = false) {
   PhaseHost &ph = p->phases[p->c->sh_phase];
   const PhaseDev &P = ph.dev;
   if (start_state > P.Q) return KEX_ERR_ARG;
@@ -1948,8 +1951,47 @@ static int shard_walk_seam(kex_program *p, uint32_t start_state, uint32_t *end_s
     for (uint32_t r = 0; r < nseam; ++r) h_seam[r] = (uint8_t)r;
     return KEX_OK;
   }
-  int rc = do_walk(p, start_state, st);
-  if (rc) return rc;
+  int rc;
+  // G-mode tail evaluation of a shard (see run_phase): k3_seams and the live-set tree over the last
+  // tiles only.  The shard's seam summary -- how the live set at its end maps to its start -- is
+  // then the constant map to G[start state], provided the tail's own summary is a constant map
+  // whose value is G[state at the tail's start] (the anchor) and every tile before the tail is
+  // G-consistent; the latter is only known after the emit, which reports KEX_RETRY_EXACT if not.
+  const bool regs = ph.fast && ph.fdev.NL > 1;
+  if (allow_tail && ph.v4.ok && !ph.v4_off && ph.v4_learned && ph.v4_tail_ok && start_state != P.Q &&
+      (!regs || (ph.h_G.size() == (size_t)P.Q + 1 && ph.h_G[start_state] != 0xFF)) && !getenv("KEX_V4_NOTAIL") &&
+      !getenv("KEX_V4_EXACT")) {
+    const size_t ntiles_all = (p->c->sh_n + V3_TILE - 1) / V3_TILE;
+    if (ntiles_all >= 4 * V4_TAIL_TILES) {
+      const size_t tail_first = (ntiles_all - V4_TAIL_TILES) / V3_TPC * V3_TPC;
+      if ((rc = do_walk_fast(p, start_state, st, tail_first))) return rc;
+      if (p->c->res_host->fail_pos == KEX_NONE64 && p->c->res_host->end_state != P.Q && !regs) {
+        // no registers: nothing to stitch, the tail walk was only needed to see a failure
+        *fail_pos = (size_t)-1;
+        *end_state = p->c->res_host->end_state;
+        for (uint32_t r = 0; r < nseam; ++r) h_seam[r] = (uint8_t)r;
+        return KEX_OK;
+      }
+      if (p->c->res_host->fail_pos == KEX_NONE64 && p->c->res_host->end_state != P.Q) {
+        size_t cnt[8];
+        int nl = 0;
+        if ((rc = lam_up(p, ntiles_all - tail_first, cnt, &nl, st))) return rc;
+        std::vector<uint8_t> bt(nseam);
+        uint16_t s0 = 0;
+        if ((rc = fetch_sync(p, bt.data(), p->c->bmaps[nl - 1].p, nseam, st))) return rc;
+        if ((rc = fetch_sync(p, &s0, (const uint16_t *)p->c->starts[0].p + tail_first / V3_TPC, sizeof(s0), st))) return rc;
+        bool constant = true;
+        for (uint32_t r = 1; r < nseam; ++r) constant = constant && bt[r] == bt[0];
+        if (constant && s0 <= P.Q && ph.h_G[s0] == bt[0]) {
+          *fail_pos = (size_t)-1;
+          *end_state = p->c->res_host->end_state;
+          for (uint32_t r = 0; r < nseam; ++r) h_seam[r] = ph.h_G[start_state];
+          return KEX_OK;
+        }
+      }
+    }
+  }
+  if ((rc = do_walk(p, start_state, st))) return rc;
   const unsigned long long f = p->c->res_host->fail_pos;
   *fail_pos = (f == KEX_NONE64) ? (size_t)-1 : (size_t)f;
   *end_state = p->c->res_host->end_state;
@@ -1971,7 +2013,13 @@ extern "C" int kex_shard_walk(kex_program *p, uint32_t start_state, uint32_t *en
                               uint8_t *h_seam, void *stream) {
   if (!p || !end_state || !fail_pos || !h_seam) return KEX_ERR_ARG;
   CK(cudaSetDevice(p->device));
-  return shard_walk_seam(p, start_state, end_state, fail_pos, h_seam, (cudaStream_t)stream);
+  return shard_walk_seam(p, start_state, end_state, fail_pos, h_seam, (cudaStream_t)stream, p->shard_tail);
+}
+
+extern "C" int kex_set_shard_tail(kex_program *p, int enabled) {
+  if (!p) return KEX_ERR_ARG;
+  p->shard_tail = enabled != 0;
+  return KEX_OK;
 }
 
 // Seam codes at the end of every shard from the shards' seam summaries (in
@@ -2003,7 +2051,14 @@ extern "C" int kex_shard_emit(kex_program *p, uint32_t live_end_mask, size_t n_e
                               size_t *out_len, void *stream) {
   if (!p || !out_len || n_eff > p->c->sh_n) return KEX_ERR_ARG;
   CK(cudaSetDevice(p->device));
-  const int rc = do_emit(p, live_end_mask, n_eff, d_out, out_cap, out_len, (cudaStream_t)stream);
+  int rc = do_emit(p, live_end_mask, n_eff, d_out, out_cap, out_len, (cudaStream_t)stream);
+  if (rc == KEX_NEED_EXACT) {
+    // only reachable after kex_set_shard_tail: the shard's seam summary was given under an assumption
+    // that did not hold; this program evaluates exactly from now on, the caller repeats the shard steps
+    p->phases[p->c->sh_phase].v4_tail_ok = false;
+    *out_len = 0;
+    return KEX_RETRY_EXACT;
+  }
   if (rc == KEX_OK && p->timing && p->ev_ok && cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess) {
     // kernel times of this shard's three steps (kex_last_kernel_ms): forward, seams, emit
     if (cudaEventElapsedTime(&p->ms[0], p->ev[0], p->ev[1]) != cudaSuccess) p->ms[0] = 0.f;

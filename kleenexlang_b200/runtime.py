@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # KEX_LIB: an alternative build of the same library (kernel experiments: scripts/build_exp.py)
 LIB_PATH = os.environ.get("KEX_LIB") or os.path.join(HERE, "libkexcuda.so")
 
-KEX_OK, KEX_ERR_OUT_CAP, KEX_ERR_UNSUPPORTED = 0, -3, -4
+KEX_OK, KEX_ERR_OUT_CAP, KEX_ERR_UNSUPPORTED, KEX_RETRY_EXACT = 0, -3, -4, 1
 ACCEPT, REJECT = 0, 1
 
 _lib = None
@@ -34,7 +34,7 @@ class KexInfo(ctypes.Structure):
 EXPORTS = ["kex_load", "kex_free", "kex_info", "kex_run_device", "kex_run_host", "kex_shard_summarize",
            "kex_seam_bytes", "kex_shard_walk", "kex_stitch_live", "kex_shard_emit", "kex_final_action", "kex_out_bound",
            "kex_select_phase", "kex_stream_begin", "kex_stream_feed", "kex_stream_end", "kex_last_launch_count",
-           "kex_set_timing", "kex_last_kernel_ms", "kex_strerror", "kex_last_cuda_error"]
+           "kex_set_timing", "kex_last_kernel_ms", "kex_strerror", "kex_last_cuda_error", "kex_set_shard_tail"]
 
 
 def lib():
@@ -74,6 +74,7 @@ def lib():
     L.kex_last_launch_count.argtypes = [vp]
     L.kex_last_launch_count.restype = u32
     L.kex_set_timing.argtypes = [vp, ctypes.c_int]
+    L.kex_set_shard_tail.argtypes = [vp, ctypes.c_int]
     L.kex_last_kernel_ms.argtypes = [vp, u32]
     L.kex_last_kernel_ms.restype = ctypes.c_float
     L.kex_strerror.argtypes = [ctypes.c_int]
@@ -244,11 +245,21 @@ class CompiledProgram:
         self._check(self._L.kex_stitch_live(self._h, b"".join(seams), n, final_code, codes))
         return list(codes)
 
+    def set_shard_tail(self, on=True):
+        """Opt in to the G-mode tail evaluation for the sharded entry points
+        (include/kexcuda.h kex_set_shard_tail): `shard_emit` may then return
+        None = every rank repeats walk -> exchange -> stitch -> emit."""
+        self._check(self._L.kex_set_shard_tail(self._h, 1 if on else 0))
+
     def shard_emit(self, seam_code: int, n_eff: int, d_out: int, out_cap: int, stream: int = 0):
+        """-> output length, or None when the shard steps must be repeated
+        (KEX_RETRY_EXACT, only after `set_shard_tail`)."""
         ol = ctypes.c_size_t()
         rc = self._L.kex_shard_emit(self._h, seam_code, n_eff, d_out, out_cap, ctypes.byref(ol), stream)
         if rc == KEX_ERR_OUT_CAP:
             raise KexError(rc, "output buffer too small: need %d bytes" % ol.value)
+        if rc == KEX_RETRY_EXACT:
+            return None
         self._check(rc)
         return ol.value
 

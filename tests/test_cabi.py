@@ -25,7 +25,10 @@ def test_no_cpu_fallback_in_product_path():
         for f in fs:
             if f.endswith((".py", ".cu", ".h")):
                 txt = open(os.path.join(dp, f), encoding="utf-8").read()
-                assert "import oracle" not in txt and "from oracle" not in txt and "kex_oracle" not in txt, f
+                # the top-level `oracle` package (test infrastructure), as a module -- not the package's own
+                # frontend/oracle_action.py, which restates the reference's *oracle machine* (OracleMachine.hs)
+                assert not re.search(r"^\s*(import|from)\s+oracle(\.|\s|$)", txt, re.M), f
+                assert "kex_oracle" not in txt and "libkexoracle" not in txt, f
 
 
 def test_error_strings():

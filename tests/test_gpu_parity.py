@@ -458,3 +458,47 @@ def test_block_streaming_unsupported_program():
     with pytest.raises(KexError) as ei:
         prog.run_stream(iter([b"ab"]), lambda b: None)
     assert ei.value.code == -4
+
+
+@pytest.mark.parametrize("name", ["csv2json", "fastq2fasta"])
+@pytest.mark.parametrize("force_retry", [False, True])
+def test_sharded_tail_evaluation(name, force_retry, monkeypatch):
+    """kex_set_shard_tail: three shards of 2 MiB cut at arbitrary positions,
+    evaluated twice -- the first round learns G (exact live sets everywhere),
+    the second uses the tail evaluation: the seam summary is the constant map
+    to G[start state] and kex_shard_emit verifies it.  With KEX_V4_TAIL_TEST the
+    kernel reports a broken induction: every shard repeats walk / stitch / emit
+    (KEX_RETRY_EXACT) and the library evaluates exactly from then on."""
+    import torch
+    from kleenexlang_b200.runtime import CompiledProgram
+    from kleenexlang_b200.sharding import stitch_states, stitch_live
+    if force_retry:
+        monkeypatch.setenv("KEX_V4_TAIL_TEST", "1")
+    blob = compile_kex(program_source(name))
+    ssts = build_ssts(program_source(name))
+    d = workloads.GENERATORS[name](6 << 20, seed=4).tobytes()
+    cuts = [0, 2 * 1048576 + 77777, 4 * 1048576 + 1234, len(d)]
+    shards = [d[cuts[i]:cuts[i + 1]] for i in range(3)]
+    progs = [CompiledProgram(blob) for _ in shards]
+    for p in progs:
+        p.set_shard_tail(True)
+    bufs = [torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda() for s in shards]
+    outs_buf = [torch.empty(6 * b.numel() + 64, dtype=torch.uint8, device="cuda") for b in bufs]
+    expect = oracle_run(ssts, d)
+    retried = 0
+    for rnd in range(3):
+        maps = [p.shard_summarize(b.data_ptr(), b.numel()) for p, b in zip(progs, bufs)]
+        starts = stitch_states(maps, ssts[0].initial)
+        while True:
+            walks = [p.shard_walk(s) for p, s in zip(progs, starts)]
+            assert all(w[1] is None for w in walks)
+            acc, code, tail = progs[-1].final_action(walks[-1][0])
+            lives = stitch_live(progs[0], [w[2] for w in walks], code)
+            lens = [p.shard_emit(live, b.numel(), o.data_ptr(), o.numel()) for p, b, o, live in zip(progs, bufs, outs_buf, lives)]
+            if all(n is not None for n in lens):
+                break
+            retried += 1
+            assert retried < 4
+        got = b"".join(bytes(o[:n].cpu().numpy()) for o, n in zip(outs_buf, lens)) + tail
+        assert (0, got) == expect[:2], rnd
+    assert (retried > 0) == (force_retry and progs[0].info()["emit_kernel"] == 4)
