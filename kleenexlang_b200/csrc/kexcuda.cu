@@ -1016,6 +1016,7 @@ static int load_v4(kex_program *p, PhaseHost &ph, const uint8_t *f, uint32_t fl,
   v.o_warp = sp;
   if (sp + 8u * (2048u + 128u + V4_RECCAP * 8u) > (uint32_t)V3_SMEM_MAX) return KEX_OK;
   v.rmw = (min_tpl >= 3u || NT == 0u) ? 1u : 0u;
+  if (getenv("KEX_V4_NORMW")) v.rmw = 0u;              // knob: byte stores at the template edges (tests, timing)
   ph.h_trans2.assign(trans2, trans2 + (size_t)Q1 * C);
   ph.h_BE.assign(BE, BE + (size_t)NL * A);
   ph.g_static.assign(f + oG, f + oG + Q1);

@@ -285,7 +285,8 @@ V4_PROGS = ["csv2json", "fastq2fasta"]      # iso_datetime: 37 x 14 entries do n
 
 @pytest.mark.parametrize("name", PROGS)
 @pytest.mark.parametrize("knob", [{}, {"KEX_V4_EXACT": "1"}, {"KEX_V4_STAGE": "256", "KEX_V4_RECCAP": "8"}, {"KEX_NO_V4": "1"},
-                                  {"KEX_V3_WORKERS": "3"}, {"KEX_V4_LOG6": "1"}, {"KEX_V4_NOTAIL": "1"}, {"KEX_V4_TAIL_TEST": "1"}])
+                                  {"KEX_V3_WORKERS": "3"}, {"KEX_V4_LOG6": "1"}, {"KEX_V4_NOTAIL": "1"}, {"KEX_V4_TAIL_TEST": "1"},
+                                  {"KEX_V4_NORMW": "1"}])
 def test_v4_paths_forced(name, knob, monkeypatch):
     """The G-mode emit kernel (kex_v4.cuh) and its rarely taken paths, forced:
     every tile evaluated exactly from the tables in global memory
