@@ -221,13 +221,16 @@ def run_reference_arm(args, cfg):
                 dt, nb = time_oracle_port(cfg["gen"], 32 << 20)
             if i >= args.warmup:
                 vals.append((dt, nb))
-        # the other flag sets of the reference's C back end, one pass each over the same files (the
-        # two-process variants run one instance per two cores); the line's value is the fastest
+        # the other flag sets of the reference's C back end over the same files: one warm-up pass and up
+        # to three timed ones each (the two-process variants run one instance per two cores); the line's
+        # value is the fastest flag set
         if kind == "reference":
             for v in (".la", ".act", ".default"):
                 if ref_binary(v):
                     fs = files if v == ".la" else files[:max(1, cores // 2)]
-                    dt = run_reference_once(fs, v)
+                    run_reference_once(fs, v)                                   # warm-up pass
+                    k = max(1, min(args.steps, 3))
+                    dt = sum(run_reference_once(fs, v) for _ in range(k)) / k
                     variants[VARIANT_FLAGS[v]] = (total * len(fs) / len(files)) / GIB / dt
     finally:
         for f in files:
