@@ -196,14 +196,14 @@ __device__ __forceinline__ void v4_stage_out(uint32_t stage_abs, uint32_t total,
                        __funnelshift_r(hi.z, hi.w, sh));
       *(uint4 *)(gal + 16u * c) = r;
     }
-    // head: destination bytes a..15 of chunk 0
+    // head: destination bytes a..15 of chunk 0 (fewer than 16: one step)
     const uint32_t he = (end < 16u) ? end : 16u;
-    for (uint32_t b2 = a + lane; b2 < he; b2 += 32u) gal[b2] = (uint8_t)lds_u8_v(swz4(stage_abs + b2 - a));
+    if (a + lane < he) gal[a + lane] = (uint8_t)lds_u8_v(swz4(stage_abs + lane));
   }
-  // tail: after the last whole chunk
+  // tail: after the last whole chunk (fewer than 16 bytes)
   if (c_hi >= c_lo) {
-    for (uint32_t b2 = (c_hi << 4) + lane; b2 < end; b2 += 32u)
-      if (b2 >= a) gal[b2] = (uint8_t)lds_u8_v(swz4(stage_abs + b2 - a));
+    const uint32_t b2 = (c_hi << 4) + lane;
+    if (b2 < end && b2 >= a) gal[b2] = (uint8_t)lds_u8_v(swz4(stage_abs + b2 - a));
   }
 }
 
