@@ -210,6 +210,49 @@ class SST:
         return vs
 
 
+def expand_tables(sst):
+    """Device form of an SST with table atoms (`AppendTblI`, IL.hs:37-39; the
+    `tblP[n][256]` arrays of C.hs:413-430): the device emits literals and the
+    input byte, so every transition whose update appends table[input byte] is
+    split by the value the tables take -- one transition per distinct tuple of
+    table values, the table atoms replaced by those constants (what
+    `specialize`, Determinization.hs:190-206, does for singleton predicates,
+    applied to every byte of the predicate).  The transduction is unchanged;
+    the byte classes of the phase get finer (a code table numbers the bytes of
+    its predicate, so its predicate falls apart into single bytes)."""
+    if getattr(sst, "la", False):
+        raise ValueError("table atoms of lookahead SSTs carry symbol indices: no single-symbol form")
+    edges, changed = {}, False
+    for q, es in sst.edges.items():
+        out = []
+        for p, upd, q2 in es:
+            tabs = []
+            for w in upd.values():
+                for a in w:
+                    if a[0] == "t" and a[1] not in tabs:
+                        tabs.append(a[1])
+            if not tabs:
+                out.append((p, upd, q2))
+                continue
+            changed = True
+            groups = {}
+            for b in BS.to_list(p):
+                key = tuple(t[b] for t in tabs)
+                groups[key] = groups.get(key, 0) | (1 << b)
+            for key, bs in groups.items():
+                val = dict(zip(tabs, key))
+                out.append((bs, {v: normalize_update(tuple(("c", (val[a[1]],)) if a[0] == "t" else a for a in w))
+                                 for v, w in upd.items()}, q2))
+        edges[q] = out
+    if not changed:
+        return sst
+    r = SST(sst.nstates, edges, sst.initial, sst.final, sst.nvars)
+    for k in ("action",):
+        if hasattr(sst, k):
+            setattr(r, k, getattr(sst, k))
+    return r
+
+
 # ---- lookahead (`--la=true`): longest deterministic prefixes as multi-symbol tests
 def _right_input_closure(fst, q):
     """rightInputClosure (SymbolicFST.hs:282-297): states without epsilon edges reachable over epsilon edges."""

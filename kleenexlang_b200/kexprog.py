@@ -65,6 +65,79 @@ def check_chronological(sst):
     return all(ok(w) for w in sst.final.values())
 
 
+def check_creation_order(sst, live):
+    """The device never moves register contents: the step that creates a byte
+    writes it, at the prefix sum of the surviving bytes -- sound iff the order
+    of the bytes in the output is the order of their creation.  Per update
+    that is `check_chronological`; across registers it is a property of
+    path-tree SSTs (a parent's content is older than its children's,
+    Determinization.hs:165-183) that constant propagation can break: a
+    register whose content is statically known is materialised as a literal
+    only where it is used, i.e. *later* than the contents it precedes
+    (SymbolicSST.hs:273-331).  This is the static check: a must-relation
+    older[q] over the live registers of state q (y, z) = "every byte of y was
+    created before every byte of z, or in the same step with y's pieces first
+    (pieces of a step are laid out by register number)", propagated to a
+    fixpoint; every concatenation `.. y z ..` needs (y, z), and whatever is
+    appended to the output stream must be older than everything still pending
+    in a live register.  Register 0 is the stream."""
+    NEW = -1
+
+    def atoms_of(upd, x):
+        return upd[x] if x in upd else (("v", x),)
+
+    def older(rel, a, xa, b, xb):
+        # a in the update of register xa, b in that of xb (xa != xb), both of the same step
+        ra = a[1] if a[0] == "v" else NEW
+        rb = b[1] if b[0] == "v" else NEW
+        if ra != NEW and rb != NEW:
+            return ra == 0 or (ra, rb) in rel
+        if rb == NEW:
+            return ra != NEW or xa < xb
+        return False
+
+    def transfer(rel, upd, regs2):
+        out = set()
+        lists = {x: atoms_of(upd, x) for x in regs2}
+        for x in regs2:
+            for y in regs2:
+                if x != y and all(older(rel, a, x, b, y) for a in lists[x] for b in lists[y]):
+                    out.add((x, y))
+        return out
+
+    regs = {q: sorted(live[q] | {0}) for q in range(sst.nstates)}
+    rel = {sst.initial: {(x, y) for x in regs[sst.initial] for y in regs[sst.initial] if x != y}}
+    work = [sst.initial]
+    while work:
+        q = work.pop()
+        for _, upd, q2 in sst.edges.get(q, ()):
+            r2 = transfer(rel[q], upd, regs[q2])
+            if q2 not in rel:
+                rel[q2] = r2
+                work.append(q2)
+            elif not rel[q2] <= r2:
+                rel[q2] &= r2
+                work.append(q2)
+    for q, es in sst.edges.items():
+        if q not in rel:
+            continue
+        for _, upd, q2 in es:
+            for x in regs[q2]:
+                w = atoms_of(upd, x)
+                for a, b in zip(w, w[1:]):
+                    if a[0] == "v" and b[0] == "v" and a[1] != 0 and (a[1], b[1]) not in rel[q]:
+                        return False
+            after = transfer(rel[q], upd, regs[q2])
+            if any((0, x) not in after for x in regs[q2] if x != 0):
+                return False
+    for q, w in sst.final.items():
+        if q in rel:
+            for a, b in zip(w, w[1:]):
+                if a[0] == "v" and b[0] == "v" and (a[1], b[1]) not in rel[q]:
+                    return False
+    return True
+
+
 def liveness(sst):
     """Backward dataflow: live[q] = registers whose content at state q can
     still reach the output."""
@@ -102,6 +175,9 @@ def build_phase(sst) -> PhaseTables:
     if not check_chronological(sst):
         raise UnsupportedProgram("register update not in (old registers)(new material) form")
     live = liveness(sst)
+    if not check_creation_order(sst, live):
+        raise UnsupportedProgram("bytes would not reach the output in the order of their creation "
+                                 "(a propagated constant is materialised after younger content)")
     Q = sst.nstates
     if Q >= 0xFFFF:
         raise UnsupportedProgram("too many states for 16-bit state ids")
@@ -333,6 +409,76 @@ def serialize_pipeline(phases, with_fast: bool = True) -> bytes:
     return hdr + b"".join(blobs)
 
 
+def compile_ssts(ssts, with_fast: bool = True) -> bytes:
+    """Pipeline of ready-made SSTs -> kexprog blob; table atoms (`AppendTblI`)
+    are lowered to constants per byte first (frontend/sst.py expand_tables)."""
+    from .frontend.sst import expand_tables
+    return serialize_pipeline([build_phase(expand_tables(s)) for s in ssts], with_fast)
+
+
+def compile_re(re_src: str, opt: int = 3, suppress_bits: bool = False, with_fast: bool = True) -> bytes:
+    """The regular-expression flavour on the device (`kexc compile x.re`,
+    compileCoder, Commands.hs:246-275): the oracle SST of the regex alone, one
+    phase that writes the bit-coded parse of its input."""
+    from .frontend.driver import build_coder_ssts
+    return compile_ssts(build_coder_ssts(re_src, opt, lookahead=False, suppress_bits=suppress_bits), with_fast)
+
+
+def oracle_code_phases(src: str, opt: int = 3, suppress_bits: bool = True):
+    """`kexc compile --act=true --la=false` with the reference's phase structure
+    (compileOracleAction, Commands.hs:204-244; C.hs:507-510): every pipeline
+    stage becomes an oracle phase (input -> code bytes, tables lowered to
+    constants) and an action phase (code -> output; the action machine as an
+    SST, ActionSST.hs:47-129), so that `-p N` selects the same phases as in the
+    reference's default build and the stream between them is the reference's
+    code.  A stage whose action SST is outside the device's update shape
+    (registers that are prepended to, reordered ...) keeps the split of
+    compile_kex: transducer phase + action-interpreter phase.
+    -> [PhaseTables | ActStage]"""
+    from .frontend.driver import build_transducers
+    from .frontend.oracle_action import build_oracle_action_ssts
+    from .frontend.sst import expand_tables, optimize, sst_from_fst
+    from .frontend.actions import action_stream_fst
+    phases = []
+
+    def pair_at(t, levels):
+        # as in compile_kex: where full constant propagation breaks the chronological shape of an update,
+        # the weaker levels (`--opt 1`, then none) are tried; I/O behaviour does not depend on --opt
+        built, out = {}, []
+        for k in (0, 1):
+            for o in levels:
+                if o not in built:
+                    built[o] = build_oracle_action_ssts(t, o, lookahead=False, suppress_bits=suppress_bits)
+                try:
+                    out.append(build_phase(expand_tables(built[o][k])))
+                    break
+                except UnsupportedProgram as e:
+                    err = e
+            else:
+                raise err
+        return out
+
+    for t in build_transducers(src):
+        try:
+            pair = pair_at(t, [opt] + [o for o in (1, 0) if o < opt])
+        except UnsupportedProgram:
+            if t.has_actions():
+                t2, act = action_stream_fst(t)
+                if act.nregs + 1 > DEVICE_ACT_SLOTS:
+                    raise UnsupportedProgram("%d action registers exceed the %d slots of the device action interpreter"
+                                             % (act.nregs, DEVICE_ACT_SLOTS))
+                pair = [build_phase(optimize(sst_from_fst(t2), opt)), act]
+            else:
+                pair = [build_phase(optimize(sst_from_fst(t), opt))]
+        phases += pair
+    return phases
+
+
+def compile_kex_oracle_code(src: str, opt: int = 3, suppress_bits: bool = True, with_fast: bool = True) -> bytes:
+    """-> kexprog blob of oracle_code_phases (`kexc compile --phases=reference`)."""
+    return serialize_pipeline(oracle_code_phases(src, opt, suppress_bits), with_fast)
+
+
 def compile_kex(src: str, opt: int = 3, with_fast: bool = True, actions: bool = True) -> bytes:
     """`.kex` source -> kexprog blob (the CUDA counterpart of
     `kexc compile --act=false --la=false`).  A stage with register actions
@@ -340,6 +486,11 @@ def compile_kex(src: str, opt: int = 3, with_fast: bool = True, actions: bool = 
     mode, becomes two phases here as well: a transducer phase that writes the
     action stream and an action-interpreter phase (frontend/actions.py);
     `actions=False` refuses such programs like `--act=false` does."""
+    return serialize_pipeline(kex_phases(src, opt, actions), with_fast)
+
+
+def kex_phases(src: str, opt: int = 3, actions: bool = True):
+    """The phases compile_kex serialises: [PhaseTables | ActStage]."""
     from .frontend.driver import build_ssts
     phases = []
     weaker = {}                      # SSTs at weaker optimisation levels, built on demand
@@ -372,4 +523,4 @@ def compile_kex(src: str, opt: int = 3, with_fast: bool = True, actions: bool = 
                     pass
             else:
                 raise first
-    return serialize_pipeline(phases, with_fast)
+    return phases

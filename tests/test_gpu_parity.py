@@ -503,3 +503,103 @@ def test_sharded_tail_evaluation(name, force_retry, monkeypatch):
         got = b"".join(bytes(o[:n].cpu().numpy()) for o, n in zip(outs_buf, lens)) + tail
         assert (0, got) == expect[:2], rnd
     assert (retried > 0) == (force_retry and progs[0].info()["emit_kernel"] == 4)
+
+
+# ---- the reference's register-free benchmark programs (tests/golden/reference_bench_vectors.json:
+# random walks through each program's own grammar, expected = lockstep simulation)
+def _bench_vectors():
+    import base64, json
+    vs = json.load(open(os.path.join(GOLDEN, "reference_bench_vectors.json")))
+    for v in vs:
+        v["input"], v["output"] = base64.b64decode(v["input"]), base64.b64decode(v["output"])
+    return vs
+
+
+BENCH = _bench_vectors()
+
+
+@pytest.mark.parametrize("name", sorted({v["name"] for v in BENCH}))
+def test_reference_bench_programs(name):
+    """All 41 of bench/kleenex/src/*.kex without register actions, whichever kernel family their tables
+    select (monoid v4 / v3 / CTA-tile / generic) and whichever --opt fallback compile_kex takes."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    vs = [v for v in BENCH if v["name"] == name]
+    prog = CompiledProgram(compile_kex(vs[0]["program"]))
+    for v in vs:
+        st, out, _ = prog.run(v["input"])
+        assert (st, out) == (0, v["output"]), (name, len(v["input"]))
+    # many tiles: the longest vector repeated (accepted where the grammar is a loop, else a reject
+    # somewhere inside), against the C oracle on the SSTs
+    big = max(vs, key=lambda v: len(v["input"]))["input"] * 40
+    ssts = build_ssts(vs[0]["program"], 3)
+    est, eout, ecnt = oracle_run(ssts, big)
+    st, out, cnt = prog.run(big)
+    assert (st, out) == (est, eout)
+    if st and len(ssts) == 1:
+        assert cnt == ecnt
+    prog.close()
+
+
+RE_CASES = [("(a|b)*c[0-9]+", [b"abbac2016", b"c7", b"bbbbc00", b"abx", b"c", b"", b"ab" * 5000 + b"c" + b"7" * 3000]),
+            ("(?:ab|a)(?:bc|c)?x{2,3}", [b"abxx", b"abcxxx", b"acxx", b"abxxxxx", b"abx", b"abcxxxxxx"]),
+            ("[a-z]+(,[a-z]+)*\\n", [b"ab,c,def\n", b"q\n", b"ab,,c\n", b"ab", b",".join([b"kleenex"] * 4000) + b"\n"])]
+
+
+@pytest.mark.parametrize("re_src,inputs", RE_CASES)
+@pytest.mark.parametrize("sb", [False, True])
+def test_regex_coder_on_device(re_src, inputs, sb):
+    """`kexc compile x.re` (compileCoder, Commands.hs:246-275): the device writes the bit-coded parse; the
+    coder's tables (AppendTblI) are lowered to constants per byte.  Checked against the C oracle running
+    the SST with its table atoms."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    from kleenexlang_b200.kexprog import compile_re
+    from kleenexlang_b200.frontend.driver import build_coder_ssts
+    coder = build_coder_ssts(re_src, 3, lookahead=False, suppress_bits=sb)
+    prog = CompiledProgram(compile_re(re_src, 3, suppress_bits=sb))
+    for d in inputs:
+        est, eout, ecnt = oracle_run(coder, d)
+        st, out, cnt = prog.run(d)
+        assert (st, out) == (est, eout)
+        if st:
+            assert cnt == ecnt
+    prog.close()
+
+
+@pytest.mark.parametrize("name", ["csv2json", "iso_datetime_to_json", "thousand_sep"])
+def test_oracle_code_phases_on_device(name):
+    """`kexc compile --phases=reference`: oracle phase + action phase per stage as in the reference's
+    default build; `-p 1` gives the reference's code (oracle SST with table atoms under the C oracle),
+    the whole pipeline gives what the direct SST gives."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    from kleenexlang_b200.kexprog import compile_kex_oracle_code
+    from kleenexlang_b200.frontend.driver import build_oracle_action_pipeline
+    src = program_source(name)
+    ref = build_oracle_action_pipeline(src, 3, lookahead=False, suppress_bits=True)
+    prog = CompiledProgram(compile_kex_oracle_code(src, 3, suppress_bits=True))
+    direct, ssts = gpu_prog(src)
+    d = workloads.GENERATORS[name](300000, seed=31).tobytes()
+    assert prog.run(d)[:2] == direct.run(d)[:2]
+    # a reject inside the oracle phase: its code is cut to whole 16 KiB flushes and the action phase runs on
+    # that (crt/crt.c:414-455) -- the two-phase pipeline under the C oracle is the expectation, not the direct SST
+    for data in (d, d[:100000] + b"\x01" + d[100001:], b""):
+        assert prog.run(data)[:2] == oracle_run(ref, data)[:2]
+    est, code, _ = oracle_run(ref[:1], d)
+    prog.select_phase(1)
+    assert prog.run(d)[:2] == (est, code)
+    prog.select_phase(2)
+    assert prog.run(code)[:2] == direct.run(d)[:2]
+    prog.select_phase(0)
+    prog.close()
+
+
+@pytest.mark.parametrize("v", VECS, ids=[v["name"] for v in VECS])
+def test_oracle_code_golden_vectors(v):
+    from kleenexlang_b200.runtime import CompiledProgram
+    from kleenexlang_b200.kexprog import compile_kex_oracle_code
+    try:
+        prog = CompiledProgram(compile_kex_oracle_code(v["program"], 3, suppress_bits=True))
+    except UnsupportedProgram:
+        pytest.skip("exceeds device register limit")
+    st, out, _ = prog.run(v["input"])
+    assert st == 0 and vec_matches(v, out)
+    prog.close()

@@ -191,3 +191,52 @@ def test_simulate_default_flags_and_regex_flavour(tmp_path):
     assert (r.returncode, r.stdout) == (0, bytes([0, 0, 0, 1, 1]))       # iterate, a, iterate, b, leave
     r = subprocess.run(KEXC + ["simulate", str(re_file), "--quiet"], input=b"abx", capture_output=True, cwd=ROOT, env=ENV)
     assert r.returncode == 1
+
+
+def test_compile_regex_flavour_and_reference_phases(tmp_path):
+    """`kexc compile x.re` builds the one-phase coder; `--phases=reference` builds an oracle phase and an
+    action phase per stage (what the reference's default `--act=true` compiles)."""
+    import struct
+    re_file = tmp_path / "t.re"
+    re_file.write_text("(a|b)*c[0-9]+\n")
+    out = str(tmp_path / "coder")
+    r = subprocess.run(KEXC + ["compile", str(re_file), "--out", out, "--quiet"], capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 0, r.stderr
+    blob = open(out + ".kexprog", "rb").read()
+    assert struct.unpack_from("<I", blob, 8)[0] == 1 and b"coder" in open(out + ".kexprog.info", "rb").read()
+    out2 = str(tmp_path / "pair")
+    r = subprocess.run(KEXC + ["compile", os.path.join(PROGRAMS, "csv2json.kex"), "--out", out2, "--phases=reference", "--quiet"],
+                       capture_output=True, cwd=ROOT, env=ENV)
+    assert r.returncode == 0, r.stderr
+    assert struct.unpack_from("<I", open(out2 + ".kexprog", "rb").read(), 8)[0] == 2
+    assert b"--phases=reference" in open(out2 + ".kexprog.info", "rb").read()
+
+
+@pytest.mark.gpu
+def test_regex_coder_and_reference_phase_binaries(tmp_path, launcher_kind):
+    """The binaries: the coder writes the bit-coded parse; with --phases=reference `-p 1` writes the
+    reference's oracle code and `-p 2` turns it into the output (crt/crt.c:372-467)."""
+    from kleenexlang_b200.frontend.driver import build_coder_ssts, build_oracle_action_pipeline
+    from kleenexlang_b200.frontend.sst import run_sst
+    env = dict(ENV, KEXC_LAUNCHER=launcher_kind)
+    re_file = tmp_path / "t.re"
+    re_file.write_text("(a|b)*c[0-9]+\n")
+    out = str(tmp_path / "coder")
+    assert subprocess.run(KEXC + ["compile", str(re_file), "--out", out, "--quiet"], cwd=ROOT, env=env).returncode == 0
+    want = run_sst(build_coder_ssts("(a|b)*c[0-9]+", 3, suppress_bits=True)[0], b"abbac2016")[1]
+    r = subprocess.run([out], input=b"abbac2016", capture_output=True)
+    assert (r.returncode, r.stdout) == (0, want)
+    assert subprocess.run([out], input=b"abx", capture_output=True).returncode == 1
+    out2 = str(tmp_path / "pair")
+    prog = os.path.join(PROGRAMS, "csv2json.kex")
+    assert subprocess.run(KEXC + ["compile", prog, "--out", out2, "--phases=reference", "--quiet"], cwd=ROOT, env=env).returncode == 0
+    from conftest import sample
+    d = sample("csv_sample.csv")
+    ref = build_oracle_action_pipeline(open(prog, encoding="utf-8").read(), 3, lookahead=False, suppress_bits=True)
+    code = run_sst(ref[0], d)[1]
+    r1 = subprocess.run([out2, "-p", "1"], input=d, capture_output=True)
+    assert (r1.returncode, r1.stdout) == (0, code)
+    r2 = subprocess.run([out2, "-p", "2"], input=code, capture_output=True)
+    whole = subprocess.run([out2], input=d, capture_output=True)
+    assert r2.returncode == whole.returncode == 0 and r2.stdout == whole.stdout
+    assert whole.stdout == open(os.path.join(ROOT, "tests", "golden", "csv2json_sample.out"), "rb").read()

@@ -186,3 +186,97 @@ def test_gmode_sections_in_blob():
             fl = e >> 24
             assert (e & 0xFFFF) <= t.Q and not (fl & 0x80 and fl & 0x40)
             assert not (fl & 0x80) or (fl & 0x3F) < f.NT
+
+
+# ---- table atoms on the device (AppendTblI lowered to constants per byte): the regex coder and the
+# reference's oracle/action phase structure
+RE_CASES = [("(a|b)*c[0-9]+", [b"abbac2016", b"c7", b"bbbbc00", b"abx", b"c", b""]),
+            ("(?:ab|a)(?:bc|c)?x{2,3}", [b"abxx", b"abcxxx", b"acxx", b"abxxxxx", b"abx", b"abcxxxxxx"]),
+            ("[a-z]+(,[a-z]+)*\\n", [b"ab,c,def\n", b"q\n", b"ab,,c\n", b"ab"])]
+
+
+@pytest.mark.parametrize("re_src,inputs", RE_CASES)
+@pytest.mark.parametrize("sb", [False, True])
+def test_model_regex_coder(re_src, inputs, sb):
+    """compileCoder (Commands.hs:246-275) in device form: the coder's tables expanded per byte give the
+    same code bytes as the SST with table atoms (C oracle, atom 3), accept and reject alike."""
+    from kleenexlang_b200.frontend.driver import build_coder_ssts
+    from kleenexlang_b200.frontend.sst import expand_tables, run_sst
+    coder = build_coder_ssts(re_src, 3, lookahead=False, suppress_bits=sb)
+    assert any(a[0] == "t" for es in coder[0].edges.values() for _, u, _ in es for w in u.values() for a in w) or "[" not in re_src
+    flat = [expand_tables(s) for s in coder]
+    assert not any(a[0] == "t" for es in flat[0].edges.values() for _, u, _ in es for w in u.values() for a in w)
+    tabs = [build_phase(s) for s in flat]
+    for d in inputs:
+        want = oracle_run(coder, d)
+        ok, code, _ = run_sst(flat[0], d)
+        assert ok == (want[0] == 0) and (not ok or code == want[1])       # a reject keeps whole 16 KiB flushes only
+        for chunk in (1, 4, 64):
+            assert _model_pipeline(tabs, d, chunk) == want
+
+
+@pytest.mark.parametrize("v", VECS, ids=[v["name"] for v in VECS])
+@pytest.mark.parametrize("sb", [False, True])
+def test_model_oracle_code_phases(v, sb):
+    """`--phases=reference`: oracle phase + action phase per stage (tables as constants) transduce like
+    the direct SSTs; the stream after the first phase is the reference's code (oracle SST with table atoms)."""
+    from kleenexlang_b200.kexprog import oracle_code_phases
+    from kleenexlang_b200.frontend.driver import build_oracle_action_pipeline
+    try:
+        phases = oracle_code_phases(v["program"], 3, suppress_bits=sb)
+    except UnsupportedProgram:
+        pytest.skip("exceeds device register limit")
+    assert not any(hasattr(t, "nregs") for t in phases)
+    ref = build_oracle_action_pipeline(v["program"], 3, lookahead=False, suppress_bits=sb)
+    assert len(phases) == len(ref)
+    want = oracle_run(build_ssts(v["program"], 3), v["input"])
+    got = _model_pipeline(phases, v["input"], 7)
+    assert got[:2] == want[:2]
+    code = oracle_run(ref[:1], v["input"])
+    assert _model_pipeline(phases[:1], v["input"], 7)[:2] == code[:2]
+
+
+# ---- the reference's own register-free benchmark programs on random walks through their own grammar
+def _bench_vectors():
+    import base64, json, os
+    from conftest import GOLDEN
+    vs = json.load(open(os.path.join(GOLDEN, "reference_bench_vectors.json")))
+    for v in vs:
+        v["input"], v["output"] = base64.b64decode(v["input"]), base64.b64decode(v["output"])
+    return vs
+
+
+BENCH = _bench_vectors()
+BENCH_NAMES = sorted({v["name"] for v in BENCH})
+
+
+@pytest.mark.parametrize("name", BENCH_NAMES)
+def test_model_reference_bench_programs(name):
+    """bench/kleenex/src/*.kex without register actions (scripts/gen_reference_bench_vectors.py): the device
+    tables (with the --opt fallbacks compile_kex takes) under the executable model of the kernels against
+    the lockstep simulation the vectors were made with, and the C oracle on the same SSTs."""
+    from kleenexlang_b200.kexprog import kex_phases
+    vs = [v for v in BENCH if v["name"] == name]
+    tabs = kex_phases(vs[0]["program"], 3, actions=False)
+    ssts = build_ssts(vs[0]["program"], 3)
+    for v in vs:
+        assert oracle_run(ssts, v["input"])[:2] == (0, v["output"])
+        assert _model_pipeline(tabs, v["input"], 61)[:2] == (0, v["output"])
+
+
+def test_creation_order_check():
+    """Weak constant propagation (--opt 1) can materialise a known register after younger content: the
+    update shape stays (old registers)(new material) but the bytes no longer leave in creation order --
+    build_phase must refuse (compile_kex then falls back to --opt 0)."""
+    from kleenexlang_b200.frontend.driver import build_transducers
+    from kleenexlang_b200.frontend.oracle_action import build_oracle_action_ssts
+    from kleenexlang_b200.frontend.sst import expand_tables
+    from kleenexlang_b200.kexprog import check_chronological
+    v = [v for v in load_vectors() if v["name"] == "test_compiled/newlinebug.kex"][0]
+    t = build_transducers(v["program"])[0]
+    o1 = expand_tables(build_oracle_action_ssts(t, 1, False, False)[0])
+    assert check_chronological(o1)
+    with pytest.raises(UnsupportedProgram, match="order of their creation"):
+        build_phase(o1)
+    o0 = expand_tables(build_oracle_action_ssts(t, 0, False, False)[0])
+    assert run_model(build_phase(o0), v["input"], 3)[:2] == (True, oracle_run([o0], v["input"])[1])
