@@ -424,7 +424,7 @@ def compile_re(re_src: str, opt: int = 3, suppress_bits: bool = False, with_fast
     return compile_ssts(build_coder_ssts(re_src, opt, lookahead=False, suppress_bits=suppress_bits), with_fast)
 
 
-def oracle_code_phases(src: str, opt: int = 3, suppress_bits: bool = True):
+def reference_phases(src: str, opt: int = 3, suppress_bits: bool = True):
     """`kexc compile --act=true --la=false` with the reference's phase structure
     (compileOracleAction, Commands.hs:204-244; C.hs:507-510): every pipeline
     stage becomes an oracle phase (input -> code bytes, tables lowered to
@@ -474,9 +474,9 @@ def oracle_code_phases(src: str, opt: int = 3, suppress_bits: bool = True):
     return phases
 
 
-def compile_kex_oracle_code(src: str, opt: int = 3, suppress_bits: bool = True, with_fast: bool = True) -> bytes:
-    """-> kexprog blob of oracle_code_phases (`kexc compile --phases=reference`)."""
-    return serialize_pipeline(oracle_code_phases(src, opt, suppress_bits), with_fast)
+def compile_reference_phases(src: str, opt: int = 3, suppress_bits: bool = True, with_fast: bool = True) -> bytes:
+    """-> kexprog blob of reference_phases (`kexc compile --phases=reference`)."""
+    return serialize_pipeline(reference_phases(src, opt, suppress_bits), with_fast)
 
 
 def compile_kex(src: str, opt: int = 3, with_fast: bool = True, actions: bool = True) -> bytes:

@@ -566,16 +566,16 @@ def test_regex_coder_on_device(re_src, inputs, sb):
 
 
 @pytest.mark.parametrize("name", ["csv2json", "iso_datetime_to_json", "thousand_sep"])
-def test_oracle_code_phases_on_device(name):
+def test_reference_phases_on_device(name):
     """`kexc compile --phases=reference`: oracle phase + action phase per stage as in the reference's
     default build; `-p 1` gives the reference's code (oracle SST with table atoms under the C oracle),
     the whole pipeline gives what the direct SST gives."""
     from kleenexlang_b200.runtime import CompiledProgram
-    from kleenexlang_b200.kexprog import compile_kex_oracle_code
+    from kleenexlang_b200.kexprog import compile_reference_phases
     from kleenexlang_b200.frontend.driver import build_oracle_action_pipeline
     src = program_source(name)
     ref = build_oracle_action_pipeline(src, 3, lookahead=False, suppress_bits=True)
-    prog = CompiledProgram(compile_kex_oracle_code(src, 3, suppress_bits=True))
+    prog = CompiledProgram(compile_reference_phases(src, 3, suppress_bits=True))
     direct, ssts = gpu_prog(src)
     d = workloads.GENERATORS[name](300000, seed=31).tobytes()
     assert prog.run(d)[:2] == direct.run(d)[:2]
@@ -595,9 +595,9 @@ def test_oracle_code_phases_on_device(name):
 @pytest.mark.parametrize("v", VECS, ids=[v["name"] for v in VECS])
 def test_oracle_code_golden_vectors(v):
     from kleenexlang_b200.runtime import CompiledProgram
-    from kleenexlang_b200.kexprog import compile_kex_oracle_code
+    from kleenexlang_b200.kexprog import compile_reference_phases
     try:
-        prog = CompiledProgram(compile_kex_oracle_code(v["program"], 3, suppress_bits=True))
+        prog = CompiledProgram(compile_reference_phases(v["program"], 3, suppress_bits=True))
     except UnsupportedProgram:
         pytest.skip("exceeds device register limit")
     st, out, _ = prog.run(v["input"])

@@ -217,13 +217,13 @@ def test_model_regex_coder(re_src, inputs, sb):
 
 @pytest.mark.parametrize("v", VECS, ids=[v["name"] for v in VECS])
 @pytest.mark.parametrize("sb", [False, True])
-def test_model_oracle_code_phases(v, sb):
+def test_model_reference_phases(v, sb):
     """`--phases=reference`: oracle phase + action phase per stage (tables as constants) transduce like
     the direct SSTs; the stream after the first phase is the reference's code (oracle SST with table atoms)."""
-    from kleenexlang_b200.kexprog import oracle_code_phases
+    from kleenexlang_b200.kexprog import reference_phases
     from kleenexlang_b200.frontend.driver import build_oracle_action_pipeline
     try:
-        phases = oracle_code_phases(v["program"], 3, suppress_bits=sb)
+        phases = reference_phases(v["program"], 3, suppress_bits=sb)
     except UnsupportedProgram:
         pytest.skip("exceeds device register limit")
     assert not any(hasattr(t, "nregs") for t in phases)
