@@ -520,13 +520,14 @@ __device__ __forceinline__ void v3_stage_out(uint32_t stage_abs, uint32_t total,
                                            __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh));
   }
   // head (destination bytes a..15 of chunk 0) and tail (after the last whole chunk)
+  // (fewer than 16 bytes each: one predicated step, no loop)
   if (a) {
     const uint32_t he = (end < 16u) ? end : 16u;
-    for (uint32_t b2 = a + lane; b2 < he; b2 += 32u) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
+    if (a + lane < he) gal[a + lane] = (uint8_t)lds_u8_v(swz(stage_abs + lane));
   }
   if (c_hi >= c_lo) {
-    for (uint32_t b2 = (c_hi << 4) + lane; b2 < end; b2 += 32u)
-      if (b2 >= a) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
+    const uint32_t b2 = (c_hi << 4) + lane;
+    if (b2 < end && b2 >= a) gal[b2] = (uint8_t)lds_u8_v(swz(stage_abs + b2 - a));
   }
 }
 

@@ -326,6 +326,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     const uint32_t v = i / V.pool_stride, k = i - v * V.pool_stride + v;
     smem_v3[V.o_pool + i] = (k >= 4u && k - 4u < F.pool_len) ? F.pool[k - 4u] : (uint8_t)0;
   }
+  if (tid == 0) *(uint32_t *)(smem_v3 + V.o_slots + 124u) = 0u;          // cta_max_recs (below)
   __syncthreads();
 
   const uint32_t wreg_off = V.o_warp + warp * warp_bytes;        // this warp's staging window, then its records
@@ -407,7 +408,9 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
   if ((force_exact & 64u) && blockIdx.x == 0 && tid == 0) atomicExch(&ctl->error, 2u);   // tests: a broken induction
   // ================================================================= workers
   uint32_t prev_total = 0xFFFFFFFFu;                  // tile whose staging window has not left yet
-  uint32_t max_recs = 0, slow_tiles = 0;
+  // most template records any tile of this CTA had (sizes the record slots of the next run): a word of
+  // shared memory, not a register per warp -- the loop is short of registers, not of LSU slots
+  uint32_t *cta_max_recs = (uint32_t *)(smem_v3 + V.o_slots + 124u);        // slots[0][31]: no worker 31
   const uint32_t fail_row = trans_abs + Q * row_bytes + slot4;
   for (uint32_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x, par ^= 1u) {
     const uint32_t tile = grp * nwork + warp;
@@ -484,7 +487,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       // exact evaluation from the tables in global memory (rare)
       sl = v4_slow_count(P, F, in + tbase + lo, cnt_pos, sA, lam_tile, lane);
       cntA = sl.cnt; cntB = 0; nrA = sl.nrec; nrB = 0;
-      if (active) ++slow_tiles;
+      if (active && lane == 0) atomicAdd(&ctl->ticket, 1u);      // tiles evaluated exactly (host: is G still right?)
     }
 #ifdef KEX_EXP_PAD_ALU
     {
@@ -510,9 +513,10 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       const size_t nt = (size_t)tile + (size_t)gridDim.x * nwork;
       if (nt < ntiles) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(in + nt * V3_TILE + lane * 32u));
-        if (lane < 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(samples + nt * V3_SPT + lane * 16u));
-        if (lane == 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blockpre + nt * (V3_TILE / V3_BLK)));
-        if (REGS && lane == 5u && nt >= tail_first) asm volatile("prefetch.global.L2 [%0];" ::"l"(lam_end + nt));
+        if (lane < 5u) {      // four sectors of samples, one of block prefixes
+          const uint16_t *pf = lane < 4u ? samples + nt * V3_SPT + lane * 16u : blockpre + nt * (V3_TILE / V3_BLK);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        }
       }
     }
     __threadfence_block();
@@ -531,7 +535,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     }
     const uint32_t o_end = xs & 0xFFFFFu;                        // bytes up to and including this lane
     const uint32_t rec_excl = (xs >> 20) - (nrA + nrB);
-    max_recs = total_recs > max_recs ? total_recs : max_recs;
+    if (lane == 0) atomicMax(cta_max_recs, total_recs);
     if (total + 16u <= stage_bytes && total_recs <= reccap) {
       if (gmode && (force_exact & 2u)) {
       } else if (gmode) {
@@ -576,8 +580,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       __syncwarp();
     }
   }
-  if (lane == 0 && max_recs) atomicMax(&ctl->pad, max_recs);
-  if (lane == 0 && slow_tiles) atomicAdd(&ctl->ticket, slow_tiles);     // tiles evaluated exactly (host: is G still right?)
+  if (lane == 0) atomicMax(&ctl->pad, *(volatile uint32_t *)cta_max_recs);   // every warp after its own last update
   if (prev_total != 0xFFFFFFFFu) {
     ef_wait_bases(3u + (par ^ 1u), bar_n);
     const unsigned long long gb = bases[(par ^ 1u) * 32u + warp];

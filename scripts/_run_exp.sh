@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-(timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "oracle_code" 2>&1 | tail -25) > gpurun_out/s3_tests2.log
-cat gpurun_out/s3_tests2.log
+(for i in 1 2; do timeout 200 python scripts/emit_only_gpu.py 8; done; timeout 200 python scripts/emit_only_gpu.py 4 iso_datetime_to_json; timeout 200 python scripts/emit_only_gpu.py 8 fastq2fasta) > gpurun_out/s3_var3.log 2>&1
+cat gpurun_out/s3_var3.log
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > gpurun_out/s3_tests3.log
+cat gpurun_out/s3_tests3.log
