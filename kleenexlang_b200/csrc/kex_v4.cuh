@@ -336,6 +336,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
   volatile uint32_t *slots = (volatile uint32_t *)(smem_v3 + V.o_slots);                             // [2][32] tile totals
   volatile unsigned long long *bases = (volatile unsigned long long *)(smem_v3 + V.o_slots + 256u);  // [2][32] output offsets
   const uint32_t ngroups = (ntiles + nwork - 1u) / nwork;
+  const uint32_t nfull = (uint32_t)(n_eff / V3_TILE);           // tiles that lie entirely inside the input
   const uint32_t bar_n = blockDim.x;
   uint32_t par = 0;
 
@@ -416,10 +417,13 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     const uint32_t tile = grp * nwork + warp;
     const bool active = tile < ntiles;
     const size_t tbase = (size_t)tile * V3_TILE;
-    const uint32_t tlen = active ? (uint32_t)((n_eff - tbase < V3_TILE) ? (n_eff - tbase) : V3_TILE) : 0u;
-    const bool full = (tlen == V3_TILE);
+    const bool full = tile < nfull;                     // every tile but (at most) the last one of the input
     const uint32_t lo = lane * 32u;
-    const uint32_t cnt_pos = (lo < tlen) ? ((tlen - lo < 32u) ? (tlen - lo) : 32u) : 0u;
+    uint32_t cnt_pos = 32u;                             // bytes of this lane that lie inside the input
+    if (!full) {
+      const uint32_t tlen = active ? (uint32_t)((n_eff - tbase < V3_TILE) ? (n_eff - tbase) : V3_TILE) : 0u;
+      cnt_pos = (lo < tlen) ? ((tlen - lo < 32u) ? (tlen - lo) : 32u) : 0u;
+    }
     uint32_t w[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) w[k] = 0;
@@ -552,8 +556,11 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
       if (force_exact & 4u) {
       } else if (V.rmw) {
         for (uint32_t ph = 0; ph < 2u; ++ph) {
-          for (uint32_t r = 2u * lane + ph; r < total_recs; r += 64u)
-            v4_template_rmw(pool_abs, V.pool_stride, tpl_abs, lds_u32_v(recs_abs + 8u * r), lds_u32_v(recs_abs + 8u * r + 4u));
+          for (uint32_t r = 2u * lane + ph; r < total_recs; r += 64u) {
+            uint32_t rc0, rc1;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rc0), "=r"(rc1) : "r"(recs_abs + 8u * r) : "memory");
+            v4_template_rmw(pool_abs, V.pool_stride, tpl_abs, rc0, rc1);
+          }
           __syncwarp();
         }
       } else {

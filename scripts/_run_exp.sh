@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-( echo "== memcheck csv2json"; timeout 600 compute-sanitizer --tool memcheck python scripts/sanitize_v4_gpu.py csv2json 2>&1 | tail -6
-  echo "== racecheck csv2json"; timeout 900 compute-sanitizer --tool racecheck python scripts/sanitize_v4_gpu.py csv2json 2>&1 | tail -6
-  echo "== synccheck csv2json fastq2fasta"; timeout 600 compute-sanitizer --tool synccheck python scripts/sanitize_v4_gpu.py 2>&1 | tail -6
-) > gpurun_out/s3_sanitizer.txt 2>&1
-cat gpurun_out/s3_sanitizer.txt
+(for i in 1 2; do timeout 200 python scripts/emit_only_gpu.py 8; done; timeout 200 python scripts/emit_only_gpu.py 8 fastq2fasta) > gpurun_out/s3_var4.log 2>&1
+cat gpurun_out/s3_var4.log
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) > gpurun_out/s3_tests4.log
+cat gpurun_out/s3_tests4.log
