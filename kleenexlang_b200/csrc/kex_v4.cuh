@@ -23,9 +23,8 @@
 //                    one 8-byte record per template
 //     templates      one lane per record, whole words from the byte-shifted
 //                    pool copies; the first and last word are merged with what
-//                    the window already holds (records are handled in two
-//                    phases by parity so that neighbours never merge the same
-//                    word at once)
+//                    the window already holds (records are handled in rounds
+//                    such that neighbours never merge the same word at once)
 //     stage-out      16-byte LDS + 16-byte STG aligned to the destination (the
 //                    swizzle permutes 16-byte chunks inside a 128-byte row)
 //   Any other tile (the last rows of the input, tiles that would overflow the
@@ -551,12 +550,18 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
         v4_slow_write(P, F, in + tbase + lo, cnt_pos, sA, sl.lam_end, stage_abs + o_end, recs_abs + 8u * (rec_excl + nrA), nullptr);
       }
       __syncwarp();
-      // ---- templates: one lane per record.  Merging variant: even records, then odd ones (two
-      // neighbours may share a word; records two apart never do when every template has >= 3 bytes)
+      // ---- templates: one lane per record.  Merging variant: two neighbours may share a word (records
+      // two apart never do when every template has >= 3 bytes), so neighbours go in different rounds
       if (force_exact & 4u) {
       } else if (V.rmw) {
-        for (uint32_t ph = 0; ph < 2u; ++ph) {
-          for (uint32_t r = 2u * lane + ph; r < total_recs; r += 64u) {
+        // m rounds, lane l takes records l m .. l m + m - 1, one per round: neighbours (which may merge the
+        // same word) always fall into different rounds, two records of one round are at least m >= 2 apart,
+        // and ceil(total / 32) rounds keep nearly every lane busy (90 records: 3 rounds of 30 lanes, where
+        // even / odd phases of 32 lanes needed 4)
+        const uint32_t m = total_recs > 64u ? (total_recs + 31u) >> 5 : 2u;
+        for (uint32_t it = 0; it < m; ++it) {
+          const uint32_t r = lane * m + it;
+          if (r < total_recs) {
             uint32_t rc0, rc1;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rc0), "=r"(rc1) : "r"(recs_abs + 8u * r) : "memory");
             v4_template_rmw(pool_abs, V.pool_stride, tpl_abs, rc0, rc1);
