@@ -111,7 +111,13 @@ __device__ __forceinline__ void v4_write_half(const uint32_t (&w)[8], const uint
   }
 }
 
-// ---- one template record (read-modify-write edges)
+// ---- one template record (read-modify-write edges): the first and the last word are merged with what the
+// window holds (one LOP3 select each), the words in between are plain copies -- no per-word mask logic
+__device__ __forceinline__ uint32_t v4_bitsel(uint32_t a, uint32_t b, uint32_t m) {       // (a & m) | (b & ~m)
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(m), "r"(a), "r"(b));
+  return r;
+}
 __device__ __forceinline__ void v4_template_rmw(uint32_t pool_abs, uint32_t pool_stride, uint32_t tpl_abs, uint32_t rc0,
                                                 uint32_t rc1) {
   const uint32_t len = rc1 & 0xFFu, id = (rc1 >> 8) & 0x3Fu;
@@ -120,24 +126,20 @@ __device__ __forceinline__ void v4_template_rmw(uint32_t pool_abs, uint32_t pool
   const uint32_t o = rc0, oe = o + len;
   const uint32_t x = src + 4u - (o & 3u), v = x & 3u;
   const uint32_t ps = pool_abs + v * pool_stride + (x - v);
-  const uint32_t w0 = o & ~3u, nw = ((oe + 3u) >> 2) - (o >> 2);
+  const uint32_t w0 = o & ~3u, nw = ((oe + 3u) >> 2) - (o >> 2);        // >= 1 (len >= 3)
   const uint32_t mlo = 0xFFFFFFFFu << (8u * (o & 3u)), mhi = 0xFFFFFFFFu >> (8u * ((0u - oe) & 3u));
-#pragma unroll
-  for (uint32_t i = 0; i < 8; ++i) {
-    if (i < nw) {
-      const uint32_t m = (i == 0 ? mlo : 0xFFFFFFFFu) & (i + 1u == nw ? mhi : 0xFFFFFFFFu);
-      uint32_t val = lds_u32(ps + 4u * i);
-      const uint32_t da = swz4(w0 + 4u * i);
-      if (m != 0xFFFFFFFFu) val = (val & m) | (lds_u32_v(da) & ~m);
-      sts_u32(da, val);
-    }
+  {
+    const uint32_t m = (nw == 1u) ? (mlo & mhi) : mlo;
+    const uint32_t da = swz4(w0);
+    sts_u32(da, v4_bitsel(lds_u32(ps), lds_u32_v(da), m));
   }
-  for (uint32_t i = 8; i < nw; ++i) {
-    const uint32_t m = (i + 1u == nw) ? mhi : 0xFFFFFFFFu;
-    uint32_t val = lds_u32(ps + 4u * i);
-    const uint32_t da = swz4(w0 + 4u * i);
-    if (m != 0xFFFFFFFFu) val = (val & m) | (lds_u32_v(da) & ~m);
-    sts_u32(da, val);
+#pragma unroll
+  for (uint32_t i = 1; i < 8; ++i)
+    if (i + 1u < nw) sts_u32(swz4(w0 + 4u * i), lds_u32(ps + 4u * i));
+  for (uint32_t i = 8; i + 1u < nw; ++i) sts_u32(swz4(w0 + 4u * i), lds_u32(ps + 4u * i));
+  if (nw > 1u) {
+    const uint32_t da = swz4(w0 + 4u * (nw - 1u));
+    sts_u32(da, v4_bitsel(lds_u32(ps + 4u * (nw - 1u)), lds_u32_v(da), mhi));
   }
   if (hole) sts_u8(swz4(o + hole - 1u), (rc1 >> 16) & 0xFFu);
 }
