@@ -95,6 +95,14 @@ __device__ __forceinline__ uint32_t lds_u8_v(uint32_t a) {
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
+// inclusive warp scan step: the shuffle's own predicate says whether the source lane exists (SHFL + one
+// predicated add instead of SHFL + compare + select + add)
+__device__ __forceinline__ uint32_t v3_scan_step(uint32_t x, int d) {
+  uint32_t r;
+  asm volatile("{ .reg .u32 t; .reg .pred p; shfl.sync.up.b32 t|p, %1, %2, 0, 0xffffffff; @p add.u32 t, t, %1; mov.u32 %0, t; }"
+               : "=r"(r) : "r"(x), "r"(d));
+  return r;
+}
 // The live-set guess table of k3_emit is read and written without
 // synchronisation on purpose (any value is only a guess that the count pass
 // verifies); built with -DKEX_SANITIZE the helpers are not inlined, which keeps
@@ -793,10 +801,7 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
     const uint32_t v = (cntA + cntB) | ((nrA + nrB) << 20);
     uint32_t xs = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xs, d);
-      if (lane >= (uint32_t)d) xs += y;
-    }
+    for (int d = 1; d < 32; d <<= 1) xs = v3_scan_step(xs, d);
     const uint32_t tot = __shfl_sync(0xFFFFFFFFu, xs, 31);
     const uint32_t total = tot & 0xFFFFFu, total_recs = tot >> 20;
 

@@ -505,10 +505,7 @@ k4_emit(PhaseDev P, FastDev F, V4Dev V, const uint8_t *__restrict__ in, size_t n
     const uint32_t v = (cntA + cntB) | ((nrA + nrB) << 20);
     uint32_t xs = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xs, d);
-      if (lane >= (uint32_t)d) xs += y;
-    }
+    for (int d = 1; d < 32; d <<= 1) xs = v3_scan_step(xs, d);
     const uint32_t tot = __shfl_sync(0xFFFFFFFFu, xs, 31);
     const uint32_t total = tot & 0xFFFFFu, total_recs = tot >> 20;
 
