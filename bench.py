@@ -31,7 +31,7 @@ CONFIGS = {
     "csv2json": {"program": "csv2json", "gen": "csv2json", "gib": 16.0, "scaling": "weak",
                  "what": "csv2json.kex on %.2f GiB synthetic CSV per GPU (gen_csv.pl distribution)",
                  # profiles/r02_ncu_k4_full_16gib.txt: k4_emit dram read + write per launch / input bytes
-                 "emit_traffic_per_in": (19.539465 + 33.439394) / 17.179869},
+                 "emit_traffic_per_in": (19.540329 + 33.476041) / 17.179869},
     "add-commas": {"program": "add-commas", "gen": "add-commas", "gib": 4.0, "scaling": "weak",
                    "what": "add-commas.kex (README example) on %.2f GiB random digits per GPU (gen_numbers.pl, avglen 1000)",
                    "emit_traffic_per_in": None},
