@@ -458,6 +458,15 @@ def reference_phases(src: str, opt: int = 3, suppress_bits: bool = True):
                 raise err
         return out
 
+    def direct_at(fst):
+        raw = sst_from_fst(fst)
+        for o in [opt] + [o for o in (1, 0) if o < opt]:
+            try:
+                return build_phase(optimize(raw, o))
+            except UnsupportedProgram as e:
+                err = e
+        raise err
+
     for t in build_transducers(src):
         try:
             pair = pair_at(t, [opt] + [o for o in (1, 0) if o < opt])
@@ -467,9 +476,9 @@ def reference_phases(src: str, opt: int = 3, suppress_bits: bool = True):
                 if act.nregs + 1 > DEVICE_ACT_SLOTS:
                     raise UnsupportedProgram("%d action registers exceed the %d slots of the device action interpreter"
                                              % (act.nregs, DEVICE_ACT_SLOTS))
-                pair = [build_phase(optimize(sst_from_fst(t2), opt)), act]
+                pair = [direct_at(t2), act]
             else:
-                pair = [build_phase(optimize(sst_from_fst(t), opt))]
+                pair = [direct_at(t)]
         phases += pair
     return phases
 

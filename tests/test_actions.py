@@ -235,3 +235,32 @@ def test_reject_inside_an_action_stage_truncates_once():
     # truncating the intermediate stream first would have lost more
     _, twice, _ = oracle_run(ssts[1:], stream[:len(stream) // 16384 * 16384])
     assert len(twice) // 16384 * 16384 <= len(out)
+
+
+def _run_phases_model(phases, data):
+    """Device-table model (tests/gpu_model.py) for SST phases, the action-stream
+    interpreter for action-interpreter phases."""
+    from gpu_model import run_model
+    from kleenexlang_b200.frontend.actions import run_act_stream
+    for t in phases:
+        if hasattr(t, "nregs"):
+            data = run_act_stream(data)
+            if data is None:
+                return None
+        else:
+            ok, data, _ = run_model(t, data, 53)
+            if not ok:
+                return None
+    return data
+
+
+@pytest.mark.parametrize("v", REF_ACTION_VECS, ids=[v["name"] for v in REF_ACTION_VECS])
+def test_reference_phases_of_register_programs(v):
+    """`kexc compile --phases=reference` on the reference's programs with register
+    actions: a stage is an oracle phase + an action-SST phase where the device can
+    evaluate the action SST as it is (appends in creation order), else a transducer
+    phase + an action-interpreter phase; either way the committed output."""
+    from kleenexlang_b200.kexprog import reference_phases
+    phases = reference_phases(v["program"], 3, suppress_bits=True)
+    assert len(phases) >= 2
+    assert _run_phases_model(phases, v["input"]) == v["output"]

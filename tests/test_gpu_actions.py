@@ -141,3 +141,15 @@ def test_reject_inside_an_action_stage_gpu():
         exp = oracle_run(ssts, bad)
         assert exp[0] == 1 and len(exp[1]) >= 2 * 16384
         assert prog.run(bad) == exp
+
+
+@pytest.mark.parametrize("v", REF_ACTION_VECS, ids=[v["name"] for v in REF_ACTION_VECS])
+def test_reference_phases_of_register_programs_gpu(v):
+    """`--phases=reference` on the reference's programs with register actions: oracle phase + action-SST
+    phase where the device can evaluate the action SST as it is, transducer + action-interpreter phase
+    otherwise (tests/test_actions.py has the CPU-model side)."""
+    from kleenexlang_b200.runtime import CompiledProgram
+    from kleenexlang_b200.kexprog import compile_reference_phases
+    prog = CompiledProgram(compile_reference_phases(v["program"], 3, suppress_bits=True))
+    assert prog.run(v["input"])[:2] == (0, v["output"])
+    prog.close()
