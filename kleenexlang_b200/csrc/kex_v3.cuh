@@ -53,6 +53,7 @@ struct V3Dev {
   const uint32_t *be3;         // [NE]  len | T << 15 | S << 16 | (lam_before * A) << 24;  S: emits exactly the input byte
   const uint32_t *be3w;        // [NE]  write-pass copy (has_lit): a one-byte ASCII literal sits in bits 8-14 instead of a template
   uint32_t has_lit;
+  uint32_t rmw_words;          // > 0: every template record is >= 3 bytes long: edge words merged (v3_template_rmw), at most this many words per template
   const uint32_t *tpl2;        // [NE]  pool offset | length << 16 | (hole offset + 1) << 24   (entries with T)
   // forward pass
   uint32_t pair;               // 1: fwdtab is the pair table [NM][C*C], 0: [NM][C]
@@ -509,6 +510,37 @@ __device__ __forceinline__ void v3_copy_template(uint32_t pool_abs, uint32_t poo
   if (t >> 24) sts_u8(swz(o + (t >> 24) - 1u), byte);  // the hole takes the input byte
 }
 
+// The same with merged edge words instead of edge bytes (every template of the program is at least three
+// bytes long, so records two apart never share a word; neighbours are handled in different rounds): the first
+// and the last word take one LOP3 select each, the words in between are plain copies; the loop is bounded by
+// the program's longest template.  (Pool offsets include four bytes of padding: the word in front of a template exists.)
+__device__ __forceinline__ uint32_t v3_bitsel(uint32_t a, uint32_t b, uint32_t m) {       // (a & m) | (b & ~m)
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(m), "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void v3_template_rmw(uint32_t pool_abs, uint32_t pool_stride, uint32_t o, uint32_t t,
+                                                uint32_t byte, uint32_t nwmax) {
+  const uint32_t src = t & 0xFFFFu, len = (t >> 16) & 0xFFu, hole = t >> 24;
+  const uint32_t oe = o + len;
+  const uint32_t x = src - (o & 3u), v = x & 3u;
+  const uint32_t ps = pool_abs + v * pool_stride + (x - v);
+  const uint32_t w0 = o & ~3u, nw = ((oe + 3u) >> 2) - (o >> 2);
+  const uint32_t mlo = 0xFFFFFFFFu << (8u * (o & 3u)), mhi = 0xFFFFFFFFu >> (8u * ((0u - oe) & 3u));
+  {
+    const uint32_t m = (nw == 1u) ? (mlo & mhi) : mlo;
+    const uint32_t da = swz(w0);
+    sts_u32(da, v3_bitsel(lds_u32(ps), lds_u32_v(da), m));
+  }
+  for (uint32_t i = 1; i + 1u < nwmax; ++i)
+    if (i + 1u < nw) sts_u32(swz(w0 + 4u * i), lds_u32(ps + 4u * i));
+  if (nw > 1u) {
+    const uint32_t da = swz(w0 + 4u * (nw - 1u));
+    sts_u32(da, v3_bitsel(lds_u32(ps + 4u * (nw - 1u)), lds_u32_v(da), mhi));
+  }
+  if (hole) sts_u8(swz(o + hole - 1u), byte);
+}
+
 // Staging window -> global with 16-byte stores aligned to the destination:
 // destination chunk c holds output bytes [16c - a, 16c - a + 16), a = gbase mod 16.
 __device__ __forceinline__ void v3_stage_out(uint32_t stage_abs, uint32_t total, unsigned long long gbase,
@@ -596,8 +628,10 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
   for (uint32_t i = tid; i < NB * NL; i += blockDim.x) smem_v3[V.o_applyB + i] = F.applyB[i];
   for (uint32_t i = tid; i < V.NE; i += blockDim.x) *(uint32_t *)(smem_v3 + V.o_tpl2 + 4u * i) = V.tpl2[i];
   for (uint32_t i = tid; i < 4u * V.pool_stride; i += blockDim.x) {
+    // copy v, byte i holds padded-pool byte i + v; the padded pool starts with 4 zero bytes (tpl2 offsets
+    // include them), so that the word in front of a template exists in every copy (v3_template_rmw)
     const uint32_t v = i / V.pool_stride, k = i - v * V.pool_stride + v;
-    smem_v3[V.o_pool + i] = (k < F.pool_len) ? F.pool[k] : (uint8_t)0;
+    smem_v3[V.o_pool + i] = (k >= 4u && k - 4u < F.pool_len) ? F.pool[k - 4u] : (uint8_t)0;
   }
   __syncthreads();
 
@@ -842,13 +876,28 @@ k3_emit(PhaseDev P, FastDev F, V3Dev V, const uint8_t *__restrict__ in, size_t n
       v3_write<LOG, LIT>(pbw, ap, w, ELA, ELB, oA, oB, recpA, recpB);
       __syncwarp();
       // ---- templates: one lane per record
-      for (uint32_t r = lane; r < total_recs; r += 32u) {
-        const uint32_t rc = lds_u32_v(recs_abs + 8u * r), rb = lds_u32_v(recs_abs + 8u * r + 4u);
-        const uint32_t ent = (((rc >> 18) << 2) - bew_abs) >> LOG;
-        if (F.max_emit <= 3u) v3_copy_short(pool_abs, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
-        else v3_copy_template(pool_abs, V.pool_stride, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
+      if (V.rmw_words) {
+        // merged edge words: m rounds, lane l takes records l m .. l m + m - 1, one per round, so that
+        // neighbours (which may merge the same word) never run in the same round
+        const uint32_t m = total_recs > 64u ? (total_recs + 31u) >> 5 : 2u;
+        for (uint32_t it = 0; it < m; ++it) {
+          const uint32_t r = lane * m + it;
+          if (r < total_recs) {
+            const uint32_t rc = lds_u32_v(recs_abs + 8u * r), rb = lds_u32_v(recs_abs + 8u * r + 4u);
+            const uint32_t ent = (((rc >> 18) << 2) - bew_abs) >> LOG;
+            v3_template_rmw(pool_abs, V.pool_stride, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb, V.rmw_words);
+          }
+          __syncwarp();
+        }
+      } else {
+        for (uint32_t r = lane; r < total_recs; r += 32u) {
+          const uint32_t rc = lds_u32_v(recs_abs + 8u * r), rb = lds_u32_v(recs_abs + 8u * r + 4u);
+          const uint32_t ent = (((rc >> 18) << 2) - bew_abs) >> LOG;
+          if (F.max_emit <= 3u) v3_copy_short(pool_abs, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
+          else v3_copy_template(pool_abs, V.pool_stride, rc & 0x3FFFFu, lds_u32(tpl2_abs + 4u * ent), rb);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       prev_total = total;                                          // staged out after the next tile's count
     } else {
       // ---- the tile's output exceeds the staging window: byte stores to global.

@@ -792,6 +792,7 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
   // emission entries
   std::vector<uint32_t> be3(NE), be3w(NE), tpl2(NE, 0);
   bool has_lit = false;
+  uint32_t tpl_min = 0xFFFFFFFFu, tpl_max = 0;         // lengths of the templates that get records
   for (uint32_t i = 0; i < NE; ++i) {
     const uint32_t e = BE[i];
     const uint32_t lamA = (e & 0xFFFCu) / 4u, len = (e >> 16) & 0xFFu;      // lam_before * A
@@ -808,7 +809,9 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
         has_lit = true;
       } else {
         T = 1;
-        tpl2[i] = src | (len << 16) | (hole << 24);
+        tpl2[i] = (src + 4u) | (len << 16) | (hole << 24);      // the shared-memory pool has four bytes of padding in front
+        tpl_min = len < tpl_min ? len : tpl_min;
+        tpl_max = len > tpl_max ? len : tpl_max;
       }
     }
     be3[i] = len | (T << 15) | (S << 16) | (lamA << 24);
@@ -820,10 +823,14 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
       if (be3w[i] & 0x7F00u) {
         const uint32_t e = BE[i], t = e >> 24;
         be3[i] |= 0x8000u;
-        tpl2[i] = (tplinfo[2 * t] & 0xFFFFu) | (1u << 16);
+        tpl2[i] = ((tplinfo[2 * t] & 0xFFFFu) + 4u) | (1u << 16);
+        tpl_min = 1;
       }
     be3w = be3;
   }
+  // templates of at least three bytes: edge words merged instead of edge bytes (kex_v3.cuh v3_template_rmw);
+  // a template of L bytes touches at most (L + 6) / 4 words.  KEX_V3_NORMW: the byte-edge variant (tests)
+  v.rmw_words = (tpl_max > 0 && tpl_min >= 3u && !getenv("KEX_V3_NORMW")) ? (tpl_max + 6u) / 4u : 0u;
   // replicated tables must be addressable with 16 bits (2 KiB allowance for the window base)
   uint32_t log = 0;
   for (uint32_t cand : {7u, 5u}) {
@@ -846,7 +853,8 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
   v.o_applyB = sp; sp += NB * NL;
   sp = (sp + 3u) & ~3u;
   v.o_tpl2 = sp; sp += NE * 4u;
-  v.pool_stride = (F.pool_len + 7u) & ~3u;
+  if (F.pool_len + 16u > 0xFFFFu) return KEX_OK;
+  v.pool_stride = (F.pool_len + 4u + 7u) & ~3u;
   v.o_pool = sp; sp += 4u * v.pool_stride;
   sp = (sp + 15u) & ~15u;
   v.o_slots = sp; sp += 256u + 512u;

@@ -262,7 +262,8 @@ def test_large_properties_tiled(name, block_mib, reps):
 
 @pytest.mark.parametrize("name", PROGS)
 @pytest.mark.parametrize("knob", [{"KEX_V3_NOSPEC": "1"}, {"KEX_V3_STAGE": "2048", "KEX_V3_RECCAP": "8"},
-                                  {"KEX_V3_NOLIT": "1"}, {"KEX_NO_V3": "1"}])
+                                  {"KEX_V3_NOLIT": "1"}, {"KEX_NO_V3": "1"}, {"KEX_NO_V4": "1", "KEX_V3_NORMW": "1"},
+                                  {"KEX_NO_V4": "1", "KEX_V3_WORKERS": "2"}])
 def test_v3_paths_forced(name, knob, monkeypatch):
     """The rarely taken paths of the v3 kernels, forced: exact live sets for
     every tile (no guessing), tiles that do not fit the staging window / record
