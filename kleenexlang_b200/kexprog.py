@@ -44,6 +44,22 @@ PIECE_CONST, PIECE_SYM = 0, 1
 DEVICE_ACT_SLOTS = 32       # csrc/kex_act.cuh ACT_NSLOT
 
 
+def check_device_limits(t):
+    """The limits kex_load enforces on a phase (csrc/kexcuda.cu load_phase): 16-bit transition indices and
+    the shared-memory footprint of the generic kernels (transition table + action headers next to the chunk
+    buffers, 200 KiB) -- checked here so that `kexc compile` refuses instead of writing a binary that cannot load."""
+    q1c = (t.Q + 1) * t.C
+    if q1c >= 65536:
+        raise UnsupportedProgram("%d states x %d byte classes exceed the 16-bit transition index of the device" % (t.Q, t.C))
+    mask = 0 if t.R == 1 else (1 if t.R <= 8 else 4)
+    chunk, stage, nt = 4096, 20480, 128                 # KEX_CHUNK, KEX_STAGE, KEX_NT
+    emit = chunk + stage + 32 + 2 * chunk + chunk * mask + (2 * nt * 32 if mask else 0) + q1c * 4 + t.A * 4 + 256
+    walk = 256 + q1c * 4 + t.A * 4
+    if max(emit, walk) > 200 * 1024:
+        raise UnsupportedProgram("%d states x %d byte classes, %d actions: the tables exceed the device's shared memory"
+                                 % (t.Q, t.C, t.A))
+
+
 class UnsupportedProgram(Exception):
     pass
 
@@ -330,6 +346,7 @@ def build_phase(sst) -> PhaseTables:
     t.pieces = [list(a[3]) for a in actions]
     t.consts = bytes(consts)
     t.max_out_per_byte = max([sum(a[2]) for a in actions] + [1])
+    check_device_limits(t)
     return t
 
 
