@@ -254,7 +254,10 @@ def _run_phases_model(phases, data):
     return data
 
 
-@pytest.mark.parametrize("v", REF_ACTION_VECS, ids=[v["name"] for v in REF_ACTION_VECS])
+# (markdown2html and dna_regex_noalias_2 take minutes under the Python model of the tables: the GPU test
+# tests/test_gpu_actions.py::test_reference_phases_of_register_programs_gpu runs all twelve)
+@pytest.mark.parametrize("v", [v for v in REF_ACTION_VECS if v["name"] not in ("markdown2html", "dna_regex_noalias_2")],
+                         ids=[v["name"] for v in REF_ACTION_VECS if v["name"] not in ("markdown2html", "dna_regex_noalias_2")])
 def test_reference_phases_of_register_programs(v):
     """`kexc compile --phases=reference` on the reference's programs with register
     actions: a stage is an oracle phase + an action-SST phase where the device can
