@@ -833,7 +833,8 @@ static int load_v3(kex_program *p, PhaseHost &ph, const uint16_t *mulF, const ui
   v.rmw_words = (tpl_max > 0 && tpl_min >= 3u && !getenv("KEX_V3_NORMW")) ? (tpl_max + 6u) / 4u : 0u;
   // replicated tables must be addressable with 16 bits (2 KiB allowance for the window base)
   uint32_t log = 0;
-  for (uint32_t cand : {7u, 5u}) {
+  for (uint32_t cand : {7u, 6u, 5u}) {                  // one table copy per lane / per two lanes / per four lanes
+    if (cand == 6u && getenv("KEX_V3_NOLOG6")) continue;
     const size_t end = (((size_t)NB * 256 + 127) & ~(size_t)127) + ((size_t)Q1 * C + (has_lit ? 2 : 1) * (size_t)NE) * (1u << cand);
     if (end + 2048 <= 65536) { log = cand; break; }
   }
@@ -1293,6 +1294,7 @@ extern "C" int kex_load(const void *blob, size_t blob_len, int device, kex_progr
   cudaFuncSetAttribute(k3_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k3_seams, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
 #define V3_EACH(X) X(7, true, true) X(7, true, false) X(7, false, true) X(7, false, false) \
+                   X(6, true, true) X(6, true, false) X(6, false, true) X(6, false, false) \
                    X(5, true, true) X(5, true, false) X(5, false, true) X(5, false, false)
 #define V3_ATTR(L, R, T) cudaFuncSetAttribute(k3_emit<L, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_MAX);
   V3_EACH(V3_ATTR)
